@@ -1,0 +1,669 @@
+// libba_b200.so — C ABI (include/ba_gpu.h) over hand-written sm_100a kernels. No CPU fallback.
+// Host orchestration of one LM trial:
+//   ba_compute : init S | k_schur (Jacobian + point block factor + Schur accumulation) | all-reduce | factor
+//   ba_solve_try: reduced solve | camera update | k_backsub_eval (back-substitution + update + test energy) | reduce
+// Reference call sites replaced: src/Eigen_ext/BacktrackLevMarqQRChol.h:257-371 (and the MOREQR /
+// CHOLESKY counterparts), src/Optimization/BAFunctor.{h,cpp}.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ba_gpu.h"
+#include "ba_dense.cuh"
+#include "ba_qr.cuh"
+#include "ba_tile.cuh"
+
+namespace {
+
+thread_local std::string g_err = "";
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return fail(BA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ NCCL
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy && GetErrorString;
+  }
+};
+NcclApi g_nccl;
+#define NK(call)                                                                                     \
+  do {                                                                                               \
+    ncclResult_t r_ = (call);                                                                        \
+    if (r_ != ncclSuccess) return fail(BA_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------- small kernels
+using namespace ba;
+
+template <class T>
+__global__ void k_add_diag(T* __restrict__ Sv, size_t lds, int n, T diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) Sv[(size_t)i * lds + i] += diag;
+}
+
+// mode 0: energy partials; 1: + residuals out; 2: Jacobian blocks out; 3: column-norm accumulation
+template <class T, int MODE>
+__global__ void __launch_bounds__(256) k_obs(int K, const int* __restrict__ view, const int* __restrict__ point, const T* __restrict__ meas,
+                                             const T* __restrict__ cams, const T* __restrict__ X, T tau2, int M,
+                                             double* __restrict__ partials, T* __restrict__ out0, T* __restrict__ out1) {
+  __shared__ double sred[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  if (i < K) {
+    const int cidx = __ldg(view + i), pj = __ldg(point + i);
+    Cam<T> c; load_cam<T>(cams, cidx, c);
+    const T X0 = __ldg(X + 3 * (size_t)pj), X1 = __ldg(X + 3 * (size_t)pj + 1), X2 = __ldg(X + 3 * (size_t)pj + 2);
+    const T m0 = __ldg(meas + 2 * (size_t)i), m1 = __ldg(meas + 2 * (size_t)i + 1);
+    T e0, e1;
+    if (MODE <= 1) {
+      obs_residual<T>(c, X0, X1, X2, m0, m1, tau2, e0, e1);
+      if (MODE == 1) { out0[2 * (size_t)i] = e0; out0[2 * (size_t)i + 1] = e1; }
+    } else {
+      T jc[18], jp[6];
+      obs_jacobian<T>(c, X0, X1, X2, m0, m1, tau2, e0, e1, jc, jp);
+      if (MODE == 2) {
+#pragma unroll
+        for (int k = 0; k < 18; ++k) out0[18 * (size_t)i + k] = jc[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) out1[6 * (size_t)i + k] = jp[k];
+      } else {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) atomicAdd(out0 + 3 * (size_t)pj + b, jp[b] * jp[b] + jp[3 + b] * jp[3 + b]);
+#pragma unroll
+        for (int b = 0; b < 9; ++b) atomicAdd(out0 + 3 * (size_t)M + 9 * (size_t)cidx + b, jc[b] * jc[b] + jc[9 + b] * jc[9 + b]);
+      }
+    }
+    acc = (double)(e0 * e0 + e1 * e1);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sred[w];
+    partials[blockIdx.x] = s;
+  }
+}
+
+// deterministic final reduction: block b sums partials[b*count .. (b+1)*count) -> out[b]
+__global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ partials, int count, double* __restrict__ out) {
+  __shared__ double s[256];
+  const double* p = partials + (size_t)blockIdx.x * count;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < count; i += 256) acc += p[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) { if ((int)threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off]; __syncthreads(); }
+  if (threadIdx.x == 0) out[blockIdx.x] = s[0];
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) k_max(const T* __restrict__ v, int n, double* __restrict__ out) {
+  __shared__ double s[256];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) m = fmax(m, (double)v[i]);
+  s[threadIdx.x] = m;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) { if ((int)threadIdx.x < off) s[threadIdx.x] = fmax(s[threadIdx.x], s[threadIdx.x + off]); __syncthreads(); }
+  if (threadIdx.x == 0) out[0] = s[0];
+}
+
+// cams_test = update(cams, dx_cam) (update_params, BAFunctor.h:311-333) and |dx_cam|^2. One CTA.
+template <class T>
+__global__ void __launch_bounds__(1024) k_cam_update(int N, const T* __restrict__ cams, const T* __restrict__ dx_cam, T* __restrict__ cams_test,
+                                                     double* __restrict__ out_norm2) {
+  __shared__ double s[1024];
+  double acc = 0.0;
+  for (int c = threadIdx.x; c < N; c += 1024) {
+    const T* ci = cams + (size_t)c * CAM_STRIDE;
+    T* co = cams_test + (size_t)c * CAM_STRIDE;
+    T d[9];
+#pragma unroll
+    for (int b = 0; b < 9; ++b) { d[b] = dx_cam[9 * (size_t)c + b]; acc += (double)(d[b] * d[b]); }
+    T Rin[9], Rout[9];
+#pragma unroll
+    for (int b = 0; b < 9; ++b) Rin[b] = ci[b];
+    rodrigues_left<T>(d[3], d[4], d[5], Rin, Rout);
+#pragma unroll
+    for (int b = 0; b < 9; ++b) co[b] = Rout[b];
+    co[9] = ci[9] + d[0]; co[10] = ci[10] + d[1]; co[11] = ci[11] + d[2];
+    co[12] = ci[12] + d[6]; co[13] = ci[13] + d[7]; co[14] = ci[14] + d[8]; co[15] = T(0);
+  }
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) { if ((int)threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off]; __syncthreads(); }
+  if (threadIdx.x == 0) out_norm2[0] = s[0];
+}
+
+template <class T> __global__ void k_neg_copy(const T* __restrict__ a, T* __restrict__ b, int n, T sign) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = sign * a[i];
+}
+
+template <class A, class B> __global__ void k_convert(const A* __restrict__ a, B* __restrict__ b, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) b[i] = (B)a[i];
+}
+
+template <class T> struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  cudaError_t alloc(size_t count) { free(); n = count; return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)); }
+  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { free(); }
+};
+
+}  // namespace
+
+// =============================================================================================
+struct ba_handle {
+  virtual ~ba_handle() {}
+  virtual int set_state(const double*, const double*, const double*, const double*, const double*, const double*) = 0;
+  virtual int get_state(double*, double*, double*, double*, double*, double*) = 0;
+  virtual int eval(double*) = 0;
+  virtual int linearize(double*, double*, double*) = 0;
+  virtual int compute(double) = 0;
+  virtual int solve_try(double*, double*, double*) = 0;
+  virtual int accept() = 0;
+  virtual int reject() = 0;
+  virtual int get_dx(double*) = 0;
+  virtual int get_residuals(double*) = 0;
+  virtual int get_reduced(double*, double*) = 0;
+  virtual int get_jacobian(double*, double*) = 0;
+  virtual int comm_init(int, int, const void*) = 0;
+  virtual int set_bandwidth(int) = 0;
+  int bw = 0;
+  bool keep_reduced = false;
+  bool profiling = false;
+  long long launches = 0;
+  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+template <class T>
+struct Impl : ba_handle {
+  int N = 0, M = 0, K = 0, device = 0, variant = 0, ntiles = 0;
+  int n = 0, kd = 0;
+  T tau2 = T(0.25);
+  double lambda = 0.0;
+  bool computed = false, tried = false, linearized = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[9];
+  DevBuf<int> d_view, d_point, d_pt_start, d_tile_pt, d_info;
+  DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g */, d_keep, d_y, d_dvec, d_tmp;
+  DevBuf<T> d_qr;  // general band copy for the Householder QR of S
+  DevBuf<double> d_partials, d_scal;
+  double* h_scal = nullptr;  // pinned
+  size_t red_count = 0;      // elements of S band storage (+ g behind it)
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  int coop_grid = 0, coop_grid_qr = 0;
+
+  ~Impl() override {
+    cudaSetDevice(device);
+    if (comm) g_nccl.CommDestroy(comm);
+    if (h_scal) cudaFreeHost(h_scal);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  T* Sraw() { return d_red.p; }
+  T* Sv() { return d_red.p + kd; }
+  size_t lds() const { return (size_t)kd; }
+  T* gvec() { return d_red.p + red_count; }
+  BandMat<T> band() { return BandMat<T>{Sv(), lds(), n, kd}; }
+  static constexpr ncclDataType_t nccl_t() { return sizeof(T) == 8 ? ncclDouble : ncclFloat; }
+
+  int alloc_reduced() {
+    kd = std::min(9 * N - 1, 9 * bw + 8);
+    if (kd < 1) kd = 1;
+    n = 9 * N;
+    red_count = (size_t)n * (kd + 1);
+    CK(d_red.alloc(red_count + n));
+    CK(d_y.alloc(n)); CK(d_dvec.alloc(n));
+    if (keep_reduced) CK(d_keep.alloc(red_count + n));
+    d_qr.free();
+    return BA_OK;
+  }
+
+  int init(int N_, int M_, int K_, const int* view, const int* point, const double* meas, double tau, int variant_, int device_) {
+    N = N_; M = M_; K = K_; variant = variant_; device = device_;
+    tau2 = T(tau) * T(tau);
+    for (auto& e : ev) e = nullptr;
+    if (N <= 0 || M <= 0 || K <= 0) return fail(BA_ERR_ARG, "N, M, K must be positive");
+    // host-side structure: sortedness, ranges, CSR offsets, tiles, bandwidth
+    std::vector<int> pt_start(M + 1, 0);
+    for (int i = 0; i < K; ++i) {
+      if (view[i] < 0 || view[i] >= N || point[i] < 0 || point[i] >= M) return fail(BA_ERR_ARG, "observation %d: index out of range", i);
+      if (i > 0 && (point[i] < point[i - 1] || (point[i] == point[i - 1] && view[i] <= view[i - 1])))
+        return fail(BA_ERR_ARG, "observations must be sorted by (point, camera) without duplicates (observation %d)", i);
+      pt_start[point[i] + 1]++;
+    }
+    for (int j = 0; j < M; ++j) {
+      if (pt_start[j + 1] < 1) return fail(BA_ERR_ARG, "point %d has no observation", j);
+      if (pt_start[j + 1] > TILE) return fail(BA_ERR_ARG, "point %d has %d observations; this build supports at most %d per point", j, pt_start[j + 1], TILE);
+      pt_start[j + 1] += pt_start[j];
+    }
+    bw = 0;
+    for (int j = 0; j < M; ++j) bw = std::max(bw, view[pt_start[j + 1] - 1] - view[pt_start[j]]);
+    std::vector<int> tile_pt; tile_pt.push_back(0);
+    int cur_obs = 0, cur_pts = 0;
+    for (int j = 0; j < M; ++j) {
+      const int nj = pt_start[j + 1] - pt_start[j];
+      if (cur_obs + nj > TILE || cur_pts + 1 > TILE) { tile_pt.push_back(j); cur_obs = 0; cur_pts = 0; }
+      cur_obs += nj; cur_pts++;
+    }
+    tile_pt.push_back(M);
+    ntiles = (int)tile_pt.size() - 1;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BA_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    CK(d_view.alloc(K)); CK(d_point.alloc(K)); CK(d_pt_start.alloc(M + 1)); CK(d_tile_pt.alloc(ntiles + 1)); CK(d_info.alloc(1));
+    CK(d_meas.alloc(2 * (size_t)K));
+    CK(d_cams.alloc((size_t)N * CAM_STRIDE)); CK(d_cams_test.alloc((size_t)N * CAM_STRIDE));
+    CK(d_X.alloc(3 * (size_t)M)); CK(d_X_test.alloc(3 * (size_t)M));
+    CK(d_dx_pt.alloc(3 * (size_t)M)); CK(d_dx_cam.alloc(9 * (size_t)N));
+    const size_t npart = std::max<size_t>(3 * (size_t)ntiles, (size_t)(K + 255) / 256);
+    CK(d_partials.alloc(npart)); CK(d_scal.alloc(16));
+    CK(cudaMallocHost(&h_scal, 16 * sizeof(double)));
+    CK(cudaMemcpyAsync(d_view.p, view, K * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_point.p, point, K * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_pt_start.p, pt_start.data(), (M + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_tile_pt.p, tile_pt.data(), (ntiles + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    std::vector<T> m(2 * (size_t)K);
+    for (size_t i = 0; i < m.size(); ++i) m[i] = (T)meas[i];
+    CK(cudaMemcpyAsync(d_meas.p, m.data(), m.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(d_dx_pt.p, 0, 3 * (size_t)M * sizeof(T), stream));
+    CK(cudaMemsetAsync(d_dx_cam.p, 0, 9 * (size_t)N * sizeof(T), stream));
+    CK(cudaStreamSynchronize(stream));
+    int rc = alloc_reduced();
+    if (rc) return rc;
+    CK(cudaFuncSetAttribute(k_schur<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<T>)));
+    CK(cudaFuncSetAttribute(k_backsub_eval<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<T>)));
+    int occ = 0, sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_ldlt<T>, DENSE_THREADS, 0));
+    coop_grid = std::max(1, std::min(occ, 2)) * sms;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_qr<T>, QR_THREADS, 0));
+    coop_grid_qr = std::max(1, std::min(occ, 2)) * sms;
+    return BA_OK;
+  }
+
+  // ---- timing helpers
+  void mark(int i) { if (profiling) cudaEventRecord(ev[i], stream); }
+  void collect(int first, int last, const int* stage_of) {
+    if (!profiling) return;
+    cudaEventSynchronize(ev[last]);
+    for (int i = first; i < last; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); stage_ms[stage_of[i - first]] = ms; }
+  }
+
+  TileArgs<T> tile_args(T lam) {
+    TileArgs<T> a;
+    a.tile_pt = d_tile_pt.p; a.pt_start = d_pt_start.p; a.view = d_view.p; a.point = d_point.p; a.meas = d_meas.p;
+    a.cams = d_cams.p; a.X = d_X.p; a.tau2 = tau2; a.lambda = lam;
+    a.factor = (variant == BA_CHOLESKY) ? PF_NORMAL : PF_HOUSEHOLDER;
+    return a;
+  }
+
+  int set_state(const double* R, const double* Tt, const double* f, const double* k1, const double* k2, const double* X) override {
+    CK(cudaSetDevice(device));
+    std::vector<T> c((size_t)N * CAM_STRIDE, T(0));
+    for (int i = 0; i < N; ++i) {
+      T* o = &c[(size_t)i * CAM_STRIDE];
+      for (int b = 0; b < 9; ++b) o[b] = (T)R[9 * (size_t)i + b];
+      for (int b = 0; b < 3; ++b) o[9 + b] = (T)Tt[3 * (size_t)i + b];
+      o[12] = (T)f[i]; o[13] = (T)k1[i]; o[14] = (T)k2[i];
+    }
+    std::vector<T> x(3 * (size_t)M);
+    for (size_t i = 0; i < x.size(); ++i) x[i] = (T)X[i];
+    CK(cudaMemcpyAsync(d_cams.p, c.data(), c.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_X.p, x.data(), x.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    computed = tried = linearized = false;
+    return BA_OK;
+  }
+
+  int get_state(double* R, double* Tt, double* f, double* k1, double* k2, double* X) override {
+    CK(cudaSetDevice(device));
+    std::vector<T> c((size_t)N * CAM_STRIDE), x(3 * (size_t)M);
+    CK(cudaMemcpyAsync(c.data(), d_cams.p, c.size() * sizeof(T), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(x.data(), d_X.p, x.size() * sizeof(T), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int i = 0; i < N; ++i) {
+      const T* o = &c[(size_t)i * CAM_STRIDE];
+      for (int b = 0; b < 9; ++b) R[9 * (size_t)i + b] = (double)o[b];
+      for (int b = 0; b < 3; ++b) Tt[3 * (size_t)i + b] = (double)o[9 + b];
+      f[i] = (double)o[12]; k1[i] = (double)o[13]; k2[i] = (double)o[14];
+    }
+    for (size_t i = 0; i < x.size(); ++i) X[i] = (double)x[i];
+    return BA_OK;
+  }
+
+  int allreduce_scal(int first, int count) {
+    if (!comm) return BA_OK;
+    NK(g_nccl.AllReduce(d_scal.p + first, d_scal.p + first, count, ncclDouble, ncclSum, comm, stream));
+    return BA_OK;
+  }
+
+  int energy_pass(int slot) {
+    const int nb = (K + 255) / 256;
+    k_obs<T, 0><<<nb, 256, 0, stream>>>(K, d_view.p, d_point.p, d_meas.p, d_cams.p, d_X.p, tau2, M, d_partials.p, nullptr, nullptr);
+    k_reduce<<<1, 256, 0, stream>>>(d_partials.p, nb, d_scal.p + slot);
+    launches += 2;
+    CK(cudaGetLastError());
+    return allreduce_scal(slot, 1);
+  }
+
+  int eval(double* energy) override {
+    CK(cudaSetDevice(device));
+    int rc = energy_pass(0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_scal, d_scal.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (energy) *energy = h_scal[0];
+    return BA_OK;
+  }
+
+  int linearize(double* energy, double* max_cn2, double* max_cn) override {
+    CK(cudaSetDevice(device));
+    const int nb = (K + 255) / 256;
+    if (max_cn2 || max_cn) {
+      const size_t np = 3 * (size_t)M + 9 * (size_t)N;
+      if (d_tmp.n < np) CK(d_tmp.alloc(np));
+      CK(cudaMemsetAsync(d_tmp.p, 0, np * sizeof(T), stream));
+      k_obs<T, 3><<<nb, 256, 0, stream>>>(K, d_view.p, d_point.p, d_meas.p, d_cams.p, d_X.p, tau2, M, d_partials.p, d_tmp.p, nullptr);
+      k_reduce<<<1, 256, 0, stream>>>(d_partials.p, nb, d_scal.p + 0);
+      launches += 2;
+      if (comm) {  // camera column norms are sums over all ranks' observations
+        NK(g_nccl.AllReduce(d_tmp.p + 3 * (size_t)M, d_tmp.p + 3 * (size_t)M, 9 * (size_t)N, nccl_t(), ncclSum, comm, stream));
+      }
+      k_max<T><<<1, 256, 0, stream>>>(d_tmp.p, (int)np, d_scal.p + 5);
+      launches += 1;
+      CK(cudaGetLastError());
+      int rc = allreduce_scal(0, 1);
+      if (rc) return rc;
+      if (comm) NK(g_nccl.AllReduce(d_scal.p + 5, d_scal.p + 5, 1, ncclDouble, ncclMax, comm, stream));
+    } else {
+      int rc = energy_pass(0);
+      if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(h_scal, d_scal.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (energy) *energy = h_scal[0];
+    if (max_cn2) *max_cn2 = h_scal[5];
+    if (max_cn) *max_cn = (double)std::sqrt((T)h_scal[5]);
+    linearized = true;
+    computed = tried = false;
+    return BA_OK;
+  }
+
+  int compute(double lam) override {
+    CK(cudaSetDevice(device));
+    lambda = lam;
+    const T lamT = (T)lam;
+    const T sl = (T)std::sqrt(lamT);
+    const T diag = (variant == BA_CHOLESKY) ? lamT : sl * sl;  // QR variants square the sqrt(lambda) rows
+    mark(0);
+    CK(cudaMemsetAsync(d_red.p, 0, (red_count + n) * sizeof(T), stream));
+    if (rank == 0) { k_add_diag<T><<<(n + 255) / 256, 256, 0, stream>>>(Sv(), lds(), n, diag); launches++; }
+    mark(1);
+    k_schur<T><<<ntiles, TILE, sizeof(TileSmem<T>), stream>>>(tile_args(lamT), Sv(), lds(), gvec());
+    launches++;
+    CK(cudaGetLastError());
+    mark(2);
+    if (comm) NK(g_nccl.AllReduce(d_red.p, d_red.p, red_count + n, nccl_t(), ncclSum, comm, stream));
+    if (keep_reduced) {
+      if (d_keep.n < red_count + n) CK(d_keep.alloc(red_count + n));
+      CK(cudaMemcpyAsync(d_keep.p, d_red.p, (red_count + n) * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+    }
+    mark(3);
+    if (variant == BA_QRCHOL || variant == BA_CHOLESKY) {
+      CK(cudaMemsetAsync(d_info.p, 0, sizeof(int), stream));
+      BandMat<T> A = band();
+      T* dv = d_dvec.p; int* info = d_info.p;
+      void* args[] = {&A, &dv, &info};
+      const int nt = (n + NB - 1) / NB, bt = (kd + NB - 1) / NB;
+      const int useful = std::max(1, std::min(bt, nt) * (std::min(bt, nt) + 1) / 2);
+      const int grid = std::max(1, std::min(coop_grid, useful));
+      CK(cudaLaunchCooperativeKernel((void*)k_band_ldlt<T>, dim3(grid), dim3(DENSE_THREADS), args, 0, stream));
+      launches++;
+    } else {
+      int rc = qr_factor();
+      if (rc) return rc;
+    }
+    mark(4);
+    static const int stages[] = {0, 1, 2, 3};
+    collect(0, 4, stages);
+    if (!profiling) { /* stay asynchronous: errors surface in solve_try */ }
+    computed = true; tried = false;
+    return BA_OK;
+  }
+
+  // Householder QR of the square symmetric band matrix (QRKIT / MOREQR right block)
+  int qr_factor() {
+    const int ku = std::min(n - 1, 2 * kd);
+    const size_t ld = (size_t)kd + ku + 1;
+    if (d_qr.n < (size_t)n * ld + 2 * (size_t)n) CK(d_qr.alloc((size_t)n * ld + 2 * (size_t)n));
+    T* G = d_qr.p; T* tauv = d_qr.p + (size_t)n * ld; T* rhs = tauv + n;
+    k_band_expand<T><<<std::min<size_t>(((size_t)n * ld + 255) / 256, 65535), 256, 0, stream>>>(band(), G, ld, ku, gvec(), rhs);
+    launches++;
+    CK(cudaGetLastError());
+    QRMat<T> Q{G, ld, n, kd, ku};
+    void* args[] = {&Q, &tauv, &rhs};
+    CK(cudaLaunchCooperativeKernel((void*)k_band_qr<T>, dim3(coop_grid_qr), dim3(QR_THREADS), args, 0, stream));
+    launches++;
+    return BA_OK;
+  }
+
+  int solve_try(double* dx_norm, double* rho_den, double* energy_test) override {
+    CK(cudaSetDevice(device));
+    if (!computed) return fail(BA_ERR_STATE, "ba_solve_try called before ba_compute");
+    const T lamT = (T)lambda;
+    mark(4);
+    if (variant == BA_QRCHOL || variant == BA_CHOLESKY) {
+      // QR variants: y = S^-1 g, dx_cam = -y. CHOLESKY: g already holds b_c - W V^-1 b_p up to sign (see k_schur), same sign rule.
+      k_band_ldlt_solve<T><<<1, SOLVE_THREADS, 0, stream>>>(band(), d_dvec.p, gvec(), d_dx_cam.p, T(-1));
+      launches++;
+    } else {
+      const int ku = std::min(n - 1, 2 * kd);
+      const size_t ld = (size_t)kd + ku + 1;
+      T* G = d_qr.p; T* rhs = d_qr.p + (size_t)n * ld + n;
+      QRMat<T> Q{G, ld, n, kd, ku};
+      k_band_qr_backsolve<T><<<1, QR_SOLVE_THREADS, 0, stream>>>(Q, rhs, d_dx_cam.p, T(-1));
+      launches++;
+    }
+    CK(cudaGetLastError());
+    mark(5);
+    k_cam_update<T><<<1, 1024, 0, stream>>>(N, d_cams.p, d_dx_cam.p, d_cams_test.p, d_scal.p + 4);
+    launches++;
+    mark(6);
+    k_backsub_eval<T><<<ntiles, TILE, sizeof(TileSmem<T>), stream>>>(tile_args(lamT), d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
+                                                                      d_partials.p, ntiles);
+    launches++;
+    CK(cudaGetLastError());
+    mark(7);
+    k_reduce<<<3, 256, 0, stream>>>(d_partials.p, ntiles, d_scal.p + 1);
+    launches++;
+    int rc = allreduce_scal(1, 3);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_scal, d_scal.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h_scal + 8, d_info.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    mark(8);
+    CK(cudaStreamSynchronize(stream));
+    static const int stages[] = {4, 5, 6, 7};
+    collect(4, 8, stages);
+    const double dx2 = h_scal[2] + h_scal[4];
+    if (dx_norm) *dx_norm = std::sqrt(dx2);
+    if (rho_den) *rho_den = lambda * dx2 - h_scal[3];
+    if (energy_test) *energy_test = h_scal[1];
+    tried = true;
+    return BA_OK;
+  }
+
+  int accept() override {
+    if (!tried) return fail(BA_ERR_STATE, "ba_accept called without a trial step");
+    std::swap(d_cams.p, d_cams_test.p);
+    std::swap(d_X.p, d_X_test.p);
+    computed = tried = linearized = false;
+    return BA_OK;
+  }
+  int reject() override { tried = false; return BA_OK; }
+
+  template <class A> int d2h(const A* dev, double* host, size_t count) {
+    std::vector<A> tmp(count);
+    CK(cudaMemcpyAsync(tmp.data(), dev, count * sizeof(A), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < count; ++i) host[i] = (double)tmp[i];
+    return BA_OK;
+  }
+
+  int get_dx(double* dx) override {
+    CK(cudaSetDevice(device));
+    int rc = d2h(d_dx_pt.p, dx, 3 * (size_t)M);
+    if (rc) return rc;
+    return d2h(d_dx_cam.p, dx + 3 * (size_t)M, 9 * (size_t)N);
+  }
+
+  int get_residuals(double* r) override {
+    CK(cudaSetDevice(device));
+    if (d_tmp.n < 2 * (size_t)K) CK(d_tmp.alloc(2 * (size_t)K));
+    const int nb = (K + 255) / 256;
+    k_obs<T, 1><<<nb, 256, 0, stream>>>(K, d_view.p, d_point.p, d_meas.p, d_cams.p, d_X.p, tau2, M, d_partials.p, d_tmp.p, nullptr);
+    launches++;
+    CK(cudaGetLastError());
+    return d2h(d_tmp.p, r, 2 * (size_t)K);
+  }
+
+  int get_jacobian(double* Jc, double* Jp) override {
+    CK(cudaSetDevice(device));
+    if (d_tmp.n < 24 * (size_t)K) CK(d_tmp.alloc(24 * (size_t)K));
+    const int nb = (K + 255) / 256;
+    k_obs<T, 2><<<nb, 256, 0, stream>>>(K, d_view.p, d_point.p, d_meas.p, d_cams.p, d_X.p, tau2, M, d_partials.p, d_tmp.p, d_tmp.p + 18 * (size_t)K);
+    launches++;
+    CK(cudaGetLastError());
+    int rc = d2h(d_tmp.p, Jc, 18 * (size_t)K);
+    if (rc) return rc;
+    return d2h(d_tmp.p + 18 * (size_t)K, Jp, 6 * (size_t)K);
+  }
+
+  int get_reduced(double* S, double* g) override {
+    CK(cudaSetDevice(device));
+    if (!keep_reduced || d_keep.n < red_count + n) return fail(BA_ERR_STATE, "enable ba_keep_reduced_system before ba_compute");
+    std::vector<T> tmp(red_count + n);
+    CK(cudaMemcpyAsync(tmp.data(), d_keep.p, tmp.size() * sizeof(T), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < (size_t)n * n; ++i) S[i] = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = std::max(0, i - kd); j <= i; ++j) {
+        const double v = (double)tmp[(size_t)kd + (size_t)i * kd + j];
+        S[(size_t)i * n + j] = v; S[(size_t)j * n + i] = v;
+      }
+    for (int i = 0; i < n; ++i) g[i] = (double)tmp[red_count + i];
+    return BA_OK;
+  }
+
+  int comm_init(int rank_, int nranks_, const void* id128) override {
+    CK(cudaSetDevice(device));
+    if (!g_nccl.load()) return fail(BA_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    rank = rank_; nranks = nranks_;
+    NK(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    return BA_OK;
+  }
+
+  int set_bandwidth(int bw_) override {
+    CK(cudaSetDevice(device));
+    if (bw_ < bw) return fail(BA_ERR_ARG, "bandwidth %d smaller than this shard's own %d", bw_, bw);
+    bw = std::min(bw_, N - 1);
+    computed = tried = false;
+    return alloc_reduced();
+  }
+};
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+const char* ba_last_error(void) { return g_err.c_str(); }
+const char* ba_version(void) { return "ba_b200 0.1 (sm_100a; kernels: k_schur, k_backsub_eval, k_band_ldlt, k_band_qr)"; }
+
+int ba_create(ba_handle** out, int N, int M, int K, const int* view, const int* point, const double* meas,
+              double inlier_threshold, int precision, int variant, int device) {
+  if (!out || !view || !point || !meas) return fail(BA_ERR_ARG, "null argument");
+  if (variant < BA_QRKIT || variant > BA_CHOLESKY) return fail(BA_ERR_ARG, "unknown variant %d", variant);
+  *out = nullptr;
+  int rc;
+  if (precision == BA_F32) { auto* p = new Impl<float>(); rc = p->init(N, M, K, view, point, meas, inlier_threshold, variant, device); if (rc) { delete p; return rc; } *out = p; }
+  else if (precision == BA_F64) { auto* p = new Impl<double>(); rc = p->init(N, M, K, view, point, meas, inlier_threshold, variant, device); if (rc) { delete p; return rc; } *out = p; }
+  else return fail(BA_ERR_ARG, "unknown precision %d", precision);
+  return BA_OK;
+}
+int ba_destroy(ba_handle* h) { delete h; return BA_OK; }
+#define H_CHECK if (!h) return fail(BA_ERR_ARG, "null handle")
+int ba_comm_unique_id(void* id128) {
+  if (!g_nccl.load()) return fail(BA_ERR_NCCL, "cannot load libnccl.so.2");
+  ncclUniqueId id;
+  NK(g_nccl.GetUniqueId(&id));
+  std::memcpy(id128, &id, sizeof(id));
+  return BA_OK;
+}
+int ba_comm_init(ba_handle* h, int rank, int nranks, const void* id128) { H_CHECK; return h->comm_init(rank, nranks, id128); }
+int ba_bandwidth(ba_handle* h, int* bw) { H_CHECK; *bw = h->bw; return BA_OK; }
+int ba_set_bandwidth(ba_handle* h, int bw) { H_CHECK; return h->set_bandwidth(bw); }
+int ba_set_state(ba_handle* h, const double* R, const double* T, const double* f, const double* k1, const double* k2, const double* X) { H_CHECK; return h->set_state(R, T, f, k1, k2, X); }
+int ba_get_state(ba_handle* h, double* R, double* T, double* f, double* k1, double* k2, double* X) { H_CHECK; return h->get_state(R, T, f, k1, k2, X); }
+int ba_eval(ba_handle* h, double* energy) { H_CHECK; return h->eval(energy); }
+int ba_linearize(ba_handle* h, double* energy, double* a, double* b) { H_CHECK; return h->linearize(energy, a, b); }
+int ba_compute(ba_handle* h, double lambda) { H_CHECK; return h->compute(lambda); }
+int ba_solve_try(ba_handle* h, double* dx_norm, double* rho_den, double* energy_test) { H_CHECK; return h->solve_try(dx_norm, rho_den, energy_test); }
+int ba_accept(ba_handle* h) { H_CHECK; return h->accept(); }
+int ba_reject(ba_handle* h) { H_CHECK; return h->reject(); }
+int ba_get_dx(ba_handle* h, double* dx) { H_CHECK; return h->get_dx(dx); }
+int ba_get_residuals(ba_handle* h, double* r) { H_CHECK; return h->get_residuals(r); }
+int ba_get_reduced_system(ba_handle* h, double* S, double* g) { H_CHECK; return h->get_reduced(S, g); }
+int ba_keep_reduced_system(ba_handle* h, int enable) { H_CHECK; h->keep_reduced = enable != 0; return BA_OK; }
+int ba_get_jacobian(ba_handle* h, double* Jc, double* Jp) { H_CHECK; return h->get_jacobian(Jc, Jp); }
+int ba_launch_count(ba_handle* h, long long* launches) { H_CHECK; *launches = h->launches; return BA_OK; }
+int ba_stage_ms(ba_handle* h, double* s) { H_CHECK; for (int i = 0; i < 8; ++i) s[i] = h->stage_ms[i]; return BA_OK; }
+int ba_set_profiling(ba_handle* h, int enable) { H_CHECK; h->profiling = enable != 0; return BA_OK; }
+
+}  // extern "C"
