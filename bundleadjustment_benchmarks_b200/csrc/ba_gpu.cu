@@ -204,6 +204,8 @@ struct ba_handle {
   virtual int get_jacobian(double*, double*) = 0;
   virtual int comm_init(int, int, const void*) = 0;
   virtual int set_bandwidth(int) = 0;
+  virtual int timer_start() = 0;
+  virtual int timer_stop(double*) = 0;
   int bw = 0;
   bool keep_reduced = false;
   bool profiling = false;
@@ -222,6 +224,7 @@ struct Impl : ba_handle {
   bool computed = false, tried = false, linearized = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[9];
+  cudaEvent_t tev[2] = {nullptr, nullptr};
   DevBuf<int> d_view, d_point, d_pt_start, d_tile_pt, d_info;
   DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g */, d_keep, d_y, d_dvec, d_tmp;
   DevBuf<T> d_qr;  // general band copy for the Householder QR of S
@@ -238,6 +241,7 @@ struct Impl : ba_handle {
     if (comm) g_nccl.CommDestroy(comm);
     if (h_scal) cudaFreeHost(h_scal);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : tev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -609,6 +613,23 @@ struct Impl : ba_handle {
     return BA_OK;
   }
 
+  int timer_start() override {
+    CK(cudaSetDevice(device));
+    for (auto& e : tev) if (!e) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(tev[0], stream));
+    return BA_OK;
+  }
+  int timer_stop(double* ms) override {
+    CK(cudaSetDevice(device));
+    if (!tev[0]) return fail(BA_ERR_STATE, "ba_timer_stop without ba_timer_start");
+    CK(cudaEventRecord(tev[1], stream));
+    CK(cudaEventSynchronize(tev[1]));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, tev[0], tev[1]));
+    *ms = f;
+    return BA_OK;
+  }
+
   int set_bandwidth(int bw_) override {
     CK(cudaSetDevice(device));
     if (bw_ < bw) return fail(BA_ERR_ARG, "bandwidth %d smaller than this shard's own %d", bw_, bw);
@@ -665,5 +686,7 @@ int ba_get_jacobian(ba_handle* h, double* Jc, double* Jp) { H_CHECK; return h->g
 int ba_launch_count(ba_handle* h, long long* launches) { H_CHECK; *launches = h->launches; return BA_OK; }
 int ba_stage_ms(ba_handle* h, double* s) { H_CHECK; for (int i = 0; i < 8; ++i) s[i] = h->stage_ms[i]; return BA_OK; }
 int ba_set_profiling(ba_handle* h, int enable) { H_CHECK; h->profiling = enable != 0; return BA_OK; }
+int ba_timer_start(ba_handle* h) { H_CHECK; return h->timer_start(); }
+int ba_timer_stop(ba_handle* h, double* ms) { H_CHECK; return h->timer_stop(ms); }
 
 }  // extern "C"

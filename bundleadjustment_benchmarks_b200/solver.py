@@ -157,6 +157,14 @@ class GpuSolver:
         self._ck(self._L.ba_stage_ms(self._h, _dp(v)))
         return v
 
+    def timer_start(self):
+        self._ck(self._L.ba_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        v = C.c_double()
+        self._ck(self._L.ba_timer_stop(self._h, C.byref(v)))
+        return v.value
+
     def launches(self) -> int:
         v = C.c_longlong()
         self._ck(self._L.ba_launch_count(self._h, C.byref(v)))

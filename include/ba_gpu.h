@@ -105,6 +105,10 @@ int ba_get_jacobian(ba_handle* h, double* Jc, double* Jp);
 int ba_launch_count(ba_handle* h, long long* launches);
 int ba_stage_ms(ba_handle* h, double* stage_ms8);
 int ba_set_profiling(ba_handle* h, int enable);
+/* Whole-region device timing with CUDA events recorded on the handle's own stream (the stream every
+ * kernel of this handle is launched on): start, run any number of calls, stop -> elapsed ms. */
+int ba_timer_start(ba_handle* h);
+int ba_timer_stop(ba_handle* h, double* elapsed_ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,76 @@
+"""The kept BAL CLI (host/bundle_adjustment_large.cpp; reference: src/bundle_adjustment_large.cpp:40-176):
+usage string, return codes and before-statistics on CPU; full runs against the Python LM driver on GPU."""
+import csv
+import gzip
+import json
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "bundleadjustment_benchmarks_b200", "host")
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "survey_anchors.json")))
+
+
+@pytest.fixture(scope="module")
+def binaries():
+    from bundleadjustment_benchmarks_b200 import _lib
+    _lib.build()
+    subprocess.check_call(["make", "-C", HOST], stdout=subprocess.DEVNULL)
+    return HOST
+
+
+@pytest.fixture(scope="module")
+def p21_txt(tmp_path_factory):
+    dst = tmp_path_factory.mktemp("bal") / "problem-21-11315-pre.txt"
+    with gzip.open(os.path.join(ROOT, "data", "problem-21-11315-pre.txt.gz"), "rb") as src, open(dst, "wb") as out:
+        shutil.copyfileobj(src, out)
+    return str(dst)
+
+
+def test_usage_and_return_codes(binaries):
+    exe = os.path.join(binaries, "Bundle_Adjustment_QRChol")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage:" in r.stderr and "<sparse reconstruction file>" in r.stderr
+    r = subprocess.run([exe, "/nonexistent/file.txt"], capture_output=True, text=True)
+    assert r.returncode == 2 and "Cannot open" in r.stderr
+
+
+def test_before_statistics_match_anchors(binaries, p21_txt):
+    exe = os.path.join(binaries, "Bundle_Adjustment_QRChol")
+    r = subprocess.run([exe, p21_txt], capture_output=True, text=True, env={**os.environ, "BA_MAX_ITERS": "1"})
+    g = GOLD["problem-21-11315"]
+    assert "N(cameras) = 21, M(points) = 11315, K(measurements) = 36455" in r.stdout
+    line = [l for l in r.stdout.splitlines() if l.startswith("Mean reprojection error")][0]
+    assert abs(float(line.split(":")[1]) - g["initial_mean_reproj_px"]) < 1e-4
+    assert f"({g['initial_inliers']} / 36455 inliers)" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exe,variant,precision", [("Bundle_Adjustment_QRChol", "QRCHOL", "f64"),
+                                                   ("Bundle_Adjustment_QRKit", "QRKIT", "f64"),
+                                                   ("Bundle_Adjustment_MoreQR", "MOREQR", "f64"),
+                                                   ("Bundle_Adjustment_Cholesky", "CHOLESKY", "f64"),
+                                                   ("Bundle_Adjustment_Cholesky_f32", "CHOLESKY", "f32")])
+def test_cli_run_matches_python_driver(binaries, p21_txt, tmp_path, p21, exe, variant, precision):
+    from bundleadjustment_benchmarks_b200 import solver
+    log = str(tmp_path / "log.csv")
+    r = subprocess.run([os.path.join(binaries, exe), p21_txt], capture_output=True, text=True,
+                       env={**os.environ, "BA_MAX_ITERS": "6", "BA_LOG_CSV": log})
+    assert r.returncode == 0, r.stderr
+    assert "Backtrack LevMarq" in r.stdout and "LM finished with status: Maximum Iterations Reached" in r.stdout
+    assert " Iter         Status              f            rho         lambda        Elapsed" in r.stdout
+    rows = list(csv.DictReader(open(log)))
+    s = solver.GpuSolver(p21, variant, precision)
+    st, plog = s.minimize(max_outer=6)
+    assert len(rows) == len(plog)
+    tol = 1e-3 if precision == "f32" else 1e-7
+    for a, b in zip(rows, plog):
+        assert int(a["iter"]) == b.iter and bool(int(a["accepted"])) == b.accepted
+        assert abs(float(a["energy_test"]) - b.energy_test) / b.energy_test < tol
+    # after-statistics are printed for the committed x
+    assert r.stdout.count("Mean reprojection error") == 2
+    s.close()

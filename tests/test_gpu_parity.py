@@ -1,0 +1,217 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs. Tolerances (double): residual/Jacobian/reduced system to rounding, per-iteration cost and
+update norm to relative 1e-9 (north_star), condition-aware where the reduced system is factored by QR
+of S (cond(S) ~ 3e11 on the bundled data). Float: 1e-4 on cost and update norm for
+the LDLT variants."""
+import numpy as np
+import pytest
+
+from bundleadjustment_benchmarks_b200 import bal, solver
+from oracle.binding import Oracle
+
+pytestmark = pytest.mark.gpu
+VARIANTS = ["QRKIT", "QRCHOL", "MOREQR", "CHOLESKY"]
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+def relv(a, b):
+    return abs(a - b) / abs(b)
+
+
+@pytest.mark.parametrize("probname", ["tiny", "small", "p21", "p39"])
+def test_residual_and_jacobian(probname, request):
+    prob = request.getfixturevalue(probname)
+    s = solver.GpuSolver(prob, "QRCHOL")
+    o = Oracle(prob)
+    e, cn2, cn = o.linearize()
+    ge, gcn2, gcn = s.linearize()
+    assert relv(ge, e) < 1e-13 and relv(gcn2, cn2) < 1e-12 and relv(gcn, cn) < 1e-12
+    assert relv(s.eval(), e) < 1e-13
+    assert np.abs(s.residuals() - o.residuals()).max() < 1e-11
+    Jc, Jp = s.jacobian()
+    Jco, Jpo = o.jacobian()
+    assert rel(Jc, Jco) < 1e-11 and rel(Jp, Jpo) < 1e-11
+    s.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("probname", ["tiny", "small", "p21", "p39"])
+def test_one_step_parity(probname, variant, request):
+    prob = request.getfixturevalue(probname)
+    vid = solver.VARIANTS[variant]
+    s = solver.GpuSolver(prob, variant)
+    s.keep_reduced(True)
+    o = Oracle(prob)
+    e, cn2, cn = o.linearize()
+    lam = 1e-6 * cn if variant == "MOREQR" else 1e-12 * cn2
+    if variant == "MOREQR":
+        o.moreqr_outer()
+    ok, dxo = o.step(vid, lam)
+    assert ok
+    So, go = o.reduced()
+    s.linearize()
+    s.compute(lam)
+    dxn, rho_den, et = s.solve_try()
+    S, g = s.reduced()
+    assert rel(S, So) < 1e-11
+    assert rel(g, -go if variant == "CHOLESKY" else go) < 1e-9  # CHOLESKY oracle solves S dx = +b
+    dx = s.dx()
+    qr_right = variant in ("QRKIT", "MOREQR")
+    assert rel(dx, dxo) < (1e-7 if qr_right else 1e-8)
+    assert relv(dxn, np.linalg.norm(dxo)) < (1e-8 if qr_right else 1e-9)
+    assert relv(np.linalg.norm(dx), dxn) < 1e-12
+    assert relv(et, o.energy_at(dxo)) < 1e-9
+    rho_o = float(dxo @ (lam * dxo + o.jtres()))
+    assert relv(rho_den, rho_o) < 1e-8
+    # accepting makes the test point the state: eval() must reproduce the test energy
+    s.accept()
+    assert relv(s.eval(), et) < 1e-12
+    s.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_teacher_forced_lm_parity(p21, variant):
+    """Same (x, lambda) in -> compare cost, update norm and accept decision on every trial."""
+    vid = solver.VARIANTS[variant]
+    s = solver.GpuSolver(p21, variant)
+    o = Oracle(p21)
+    lam, lam_inc = None, 2.0
+    worst_cost, worst_dx = 0.0, 0.0
+    for it in range(1, 11):
+        e, cn2, cn = s.linearize(colnorms=(it == 1))
+        o.set_state(*s.get_state())
+        eo, cn2o, cno = o.linearize()
+        assert relv(e, eo) < 1e-12
+        if it == 1:
+            lam = 1e-6 * cn if variant == "MOREQR" else 1e-12 * cn2
+        if variant == "MOREQR":
+            o.moreqr_outer()
+        while True:
+            s.compute(lam)
+            dxn, rho_den, et = s.solve_try()
+            ok, dxo = o.step(vid, lam)
+            eto = o.energy_at(dxo)
+            worst_cost = max(worst_cost, relv(et, eto))
+            worst_dx = max(worst_dx, relv(dxn, np.linalg.norm(dxo)))
+            assert (et < e) == (eto < eo)
+            if et < e:
+                rho = (e - et) / rho_den
+                lam = max(lam * max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3), 1e-10)
+                lam_inc = 2.0
+                s.accept()
+                break
+            s.reject()
+            lam *= lam_inc
+            lam_inc = lam_inc ** 1.5
+    assert worst_cost < (1e-5 if variant in ("QRKIT", "MOREQR") else 1e-9), worst_cost
+    # |dx| is condition-limited once lambda has dropped (cond(S) grows past 1e13)
+    assert worst_dx < (1e-5 if variant in ("QRKIT", "MOREQR") else 1e-6), worst_dx
+    s.close()
+
+
+@pytest.mark.parametrize("variant", ["QRCHOL", "CHOLESKY", "QRKIT", "MOREQR"])
+def test_free_running_accept_reject_sequence(p21, variant):
+    """Free-running trajectories of GPU and oracle: same accept/reject sequence and cost to 1e-6 over
+    the first iterations (they drift apart later like any two solvers)."""
+    s = solver.GpuSolver(p21, variant)
+    st, log = s.minimize(max_outer=8)
+    sto, logo = Oracle(p21).minimize(solver.VARIANTS[variant], 8)
+    assert len(log) == len(logo)
+    for a, b in zip(log, logo):
+        assert a.iter == b.iter and bool(a.accepted) == bool(b.accepted)
+        assert relv(a.energy_test, b.energy_test) < 1e-5
+    for a, b in zip(log[:3], logo[:3]):
+        assert relv(a.energy_test, b.energy_test) < 1e-9
+        assert relv(a.dx_norm, b.dx_norm) < 1e-8
+        assert relv(a.lambda_next, b.lambda_next) < 1e-7
+    s.close()
+
+
+@pytest.mark.parametrize("variant", ["QRCHOL", "CHOLESKY"])
+def test_float_build_parity(small, p21, variant):
+    for prob in (small, p21):
+        o = Oracle(prob)  # double oracle is the yardstick; the float GPU path must stay within 1e-4
+        e, cn2, _ = o.linearize()
+        lam = 1e-12 * cn2
+        ok, dxo = o.step(solver.VARIANTS[variant], lam)
+        s = solver.GpuSolver(prob, variant, precision="f32")
+        ge, _, _ = s.linearize()
+        assert relv(ge, e) < 1e-5
+        s.compute(lam)
+        dxn, rho_den, et = s.solve_try()
+        assert relv(et, o.energy_at(dxo)) < 1e-4
+        assert relv(dxn, np.linalg.norm(dxo)) < 1e-3
+        s.close()
+
+
+def test_linear_system_residual(p39):
+    """dx solves (J^T J + lambda I) dx = -J^T r: checked with the GPU's own Jacobian, independent of the oracle."""
+    s = solver.GpuSolver(p39, "QRCHOL")
+    e, cn2, _ = s.linearize()
+    lam = 1e-12 * cn2
+    s.compute(lam)
+    s.solve_try()
+    dx = s.dx()
+    Jc, Jp = s.jacobian()
+    r = s.residuals().reshape(-1, 2)
+    M = p39.M
+    Jdx = np.einsum("kab,kb->ka", Jc, dx[3 * M:].reshape(-1, 9)[p39.view]) + np.einsum("kab,kb->ka", Jp, dx[:3 * M].reshape(-1, 3)[p39.point])
+    t = Jdx + r
+    grad = np.zeros_like(dx)
+    np.add.at(grad[:3 * M].reshape(-1, 3), p39.point, np.einsum("kab,ka->kb", Jp, t))
+    np.add.at(grad[3 * M:].reshape(-1, 9), p39.view, np.einsum("kab,ka->kb", Jc, t))
+    grad += lam * dx
+    g0 = np.zeros_like(dx)
+    np.add.at(g0[:3 * M].reshape(-1, 3), p39.point, np.einsum("kab,ka->kb", Jp, r))
+    np.add.at(g0[3 * M:].reshape(-1, 9), p39.view, np.einsum("kab,ka->kb", Jc, r))
+    assert np.linalg.norm(grad) / np.linalg.norm(g0) < 1e-7
+    s.close()
+
+
+def test_edge_cases_gpu():
+    # ragged tiles: exactly-2-observation points, bandwidth-1 matrix, more points than one tile
+    p = bal.synthetic(3, 700, seed=5, mean_obs=2.0, window=1)
+    o = Oracle(p)
+    e, cn2, _ = o.linearize()
+    s = solver.GpuSolver(p, "QRCHOL")
+    ge, _, _ = s.linearize()
+    assert relv(ge, e) < 1e-13
+    lam = 1e-9 * cn2
+    ok, dxo = o.step(1, lam)
+    s.compute(lam)
+    dxn, _, et = s.solve_try()
+    assert relv(et, o.energy_at(dxo)) < 1e-9
+    s.close()
+    # rejected input: unsorted / duplicate observations, too many observations on one point
+    bad = p.copy(); bad.view = p.view[::-1].copy(); bad.point = p.point[::-1].copy()
+    with pytest.raises(solver.BAError):
+        solver.GpuSolver(bad, "QRCHOL")
+
+
+def test_full_size_properties():
+    """BASELINE config 5 (1800 cameras / 1M points / ~5M observations): size-independent properties."""
+    prob = bal.load_named("synthetic-5m")
+    s = solver.GpuSolver(prob, "QRCHOL")
+    e, cn2, _ = s.linearize()
+    assert np.isfinite(e) and e > 0
+    assert relv(s.eval(), e) < 1e-13               # idempotent evaluation
+    lam = 1e-12 * cn2
+    s.compute(lam)
+    dxn, rho_den, et = s.solve_try()
+    assert rho_den > 0                             # predicted decrease is positive for lambda > 0
+    dx = s.dx()
+    assert relv(np.linalg.norm(dx), dxn) < 1e-12   # checksum of the step
+    s.reject()
+    s.compute(lam)                                 # same trial again: deterministic up to atomic order
+    dxn2, rho2, et2 = s.solve_try()
+    assert relv(et2, et) < 1e-10 and relv(dxn2, dxn) < 1e-9
+    big = 1e6 * lam                                # heavy damping: short step, energy must drop
+    s.reject(); s.compute(big)
+    dxn3, _, et3 = s.solve_try()
+    assert dxn3 < dxn and et3 < e
+    s.accept()
+    assert relv(s.eval(), et3) < 1e-12             # accept commits exactly the test point
+    s.close()
