@@ -22,7 +22,7 @@ SYMBOLS = [
     "ba_bandwidth", "ba_set_bandwidth", "ba_set_state", "ba_get_state", "ba_eval", "ba_linearize",
     "ba_compute", "ba_solve_try", "ba_accept", "ba_reject", "ba_get_dx", "ba_get_residuals",
     "ba_get_reduced_system", "ba_keep_reduced_system", "ba_get_jacobian", "ba_launch_count",
-    "ba_stage_ms", "ba_set_profiling", "ba_timer_start", "ba_timer_stop",
+    "ba_stage_ms", "ba_set_profiling", "ba_timer_start", "ba_timer_stop", "ba_debug_counters",
 ]
 
 _LIB = None
@@ -79,6 +79,7 @@ def lib():
     L.ba_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.ba_stage_ms.argtypes = [vp, dp]
     L.ba_set_profiling.argtypes = [vp, C.c_int]
+    L.ba_debug_counters.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.ba_timer_start.argtypes = [vp]
     L.ba_timer_stop.argtypes = [vp, dp]
     for s in SYMBOLS:

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -206,8 +207,10 @@ struct ba_handle {
   virtual int set_bandwidth(int) = 0;
   virtual int timer_start() = 0;
   virtual int timer_stop(double*) = 0;
+  virtual int debug_counters(long long*) = 0;
   int bw = 0;
   bool keep_reduced = false;
+  bool force_grid_ldlt = false;
   bool profiling = false;
   long long launches = 0;
   double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -228,7 +231,11 @@ struct Impl : ba_handle {
   DevBuf<int> d_view, d_point, d_pt_start, d_tile_pt, d_info;
   DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g */, d_keep, d_y, d_dvec, d_tmp;
   DevBuf<T> d_qr;  // general band copy for the Householder QR of S
+  DevBuf<T> d_W;   // L_kk^-1 tiles kept by the cluster LDLT for the backward pass
+  int cluster_size = 8;
+  bool solved_in_factor = false;
   DevBuf<double> d_partials, d_scal;
+  DevBuf<long long> d_dbg;
   double* h_scal = nullptr;  // pinned
   size_t red_count = 0;      // elements of S band storage (+ g behind it)
   // multi-GPU
@@ -305,7 +312,7 @@ struct Impl : ba_handle {
     CK(d_X.alloc(3 * (size_t)M)); CK(d_X_test.alloc(3 * (size_t)M));
     CK(d_dx_pt.alloc(3 * (size_t)M)); CK(d_dx_cam.alloc(9 * (size_t)N));
     const size_t npart = std::max<size_t>(3 * (size_t)ntiles, (size_t)(K + 255) / 256);
-    CK(d_partials.alloc(npart)); CK(d_scal.alloc(16));
+    CK(d_partials.alloc(npart)); CK(d_scal.alloc(16)); CK(d_dbg.alloc(16)); CK(cudaMemset(d_dbg.p, 0, 16 * sizeof(long long)));
     CK(cudaMallocHost(&h_scal, 16 * sizeof(double)));
     CK(cudaMemcpyAsync(d_view.p, view, K * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_point.p, point, K * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -325,6 +332,10 @@ struct Impl : ba_handle {
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_ldlt<T>, DENSE_THREADS, 0));
     coop_grid = std::max(1, std::min(occ, 2)) * sms;
+    if (const char* cs = std::getenv("BA_CLUSTER_SIZE")) cluster_size = std::max(1, std::min(16, atoi(cs)));
+    if (cluster_size > 8) CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (std::getenv("BA_FORCE_GRID_LDLT")) force_grid_ldlt = true;
+    CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterSmem<T>)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_qr<T>, QR_THREADS, 0));
     coop_grid_qr = std::max(1, std::min(occ, 2)) * sms;
     return BA_OK;
@@ -461,12 +472,27 @@ struct Impl : ba_handle {
     if (variant == BA_QRCHOL || variant == BA_CHOLESKY) {
       CK(cudaMemsetAsync(d_info.p, 0, sizeof(int), stream));
       BandMat<T> A = band();
-      T* dv = d_dvec.p; int* info = d_info.p;
-      void* args[] = {&A, &dv, &info};
       const int nt = (n + NB - 1) / NB, bt = (kd + NB - 1) / NB;
-      const int useful = std::max(1, std::min(bt, nt) * (std::min(bt, nt) + 1) / 2);
-      const int grid = std::max(1, std::min(coop_grid, useful));
-      CK(cudaLaunchCooperativeKernel((void*)k_band_ldlt<T>, dim3(grid), dim3(DENSE_THREADS), args, 0, stream));
+      const double flops = (double)n * kd * kd;
+      if (flops < 2e11 && !force_grid_ldlt) {
+        // latency-bound regime: one cluster, forward solve folded in, backward solve by CTA 0
+        if (d_W.n < (size_t)nt * NB * NB) CK(d_W.alloc((size_t)nt * NB * NB));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cluster_size); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = sizeof(ClusterSmem<T>); cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_band_ldlt_cluster<T>, A, d_dvec.p, d_W.p, gvec(), d_dx_cam.p, T(-1), d_info.p, d_dbg.p));
+        solved_in_factor = true;
+      } else {
+        T* dv = d_dvec.p; int* info = d_info.p;
+        void* args[] = {&A, &dv, &info};
+        const int useful = std::max(1, std::min(bt, nt) * (std::min(bt, nt) + 1) / 2);
+        const int grid = std::max(1, std::min(coop_grid, useful));
+        CK(cudaLaunchCooperativeKernel((void*)k_band_ldlt<T>, dim3(grid), dim3(DENSE_THREADS), args, 0, stream));
+        solved_in_factor = false;
+      }
       launches++;
     } else {
       int rc = qr_factor();
@@ -503,8 +529,10 @@ struct Impl : ba_handle {
     mark(4);
     if (variant == BA_QRCHOL || variant == BA_CHOLESKY) {
       // QR variants: y = S^-1 g, dx_cam = -y. CHOLESKY: g already holds b_c - W V^-1 b_p up to sign (see k_schur), same sign rule.
-      k_band_ldlt_solve<T><<<1, SOLVE_THREADS, 0, stream>>>(band(), d_dvec.p, gvec(), d_dx_cam.p, T(-1));
-      launches++;
+      if (!solved_in_factor) {
+        k_band_ldlt_solve<T><<<1, SOLVE_THREADS, 0, stream>>>(band(), d_dvec.p, gvec(), d_dx_cam.p, T(-1));
+        launches++;
+      }
     } else {
       const int ku = std::min(n - 1, 2 * kd);
       const size_t ld = (size_t)kd + ku + 1;
@@ -630,6 +658,12 @@ struct Impl : ba_handle {
     return BA_OK;
   }
 
+  int debug_counters(long long* out) override {
+    CK(cudaSetDevice(device));
+    CK(cudaMemcpy(out, d_dbg.p, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return BA_OK;
+  }
+
   int set_bandwidth(int bw_) override {
     CK(cudaSetDevice(device));
     if (bw_ < bw) return fail(BA_ERR_ARG, "bandwidth %d smaller than this shard's own %d", bw_, bw);
@@ -686,6 +720,7 @@ int ba_get_jacobian(ba_handle* h, double* Jc, double* Jp) { H_CHECK; return h->g
 int ba_launch_count(ba_handle* h, long long* launches) { H_CHECK; *launches = h->launches; return BA_OK; }
 int ba_stage_ms(ba_handle* h, double* s) { H_CHECK; for (int i = 0; i < 8; ++i) s[i] = h->stage_ms[i]; return BA_OK; }
 int ba_set_profiling(ba_handle* h, int enable) { H_CHECK; h->profiling = enable != 0; return BA_OK; }
+int ba_debug_counters(ba_handle* h, long long* out16) { H_CHECK; return h->debug_counters(out16); }
 int ba_timer_start(ba_handle* h) { H_CHECK; return h->timer_start(); }
 int ba_timer_stop(ba_handle* h, double* ms) { H_CHECK; return h->timer_stop(ms); }
 

@@ -157,6 +157,11 @@ class GpuSolver:
         self._ck(self._L.ba_stage_ms(self._h, _dp(v)))
         return v
 
+    def debug_counters(self):
+        v = (C.c_longlong * 16)()
+        self._ck(self._L.ba_debug_counters(self._h, v))
+        return list(v)
+
     def timer_start(self):
         self._ck(self._L.ba_timer_start(self._h))
 

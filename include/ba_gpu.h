@@ -107,6 +107,8 @@ int ba_stage_ms(ba_handle* h, double* stage_ms8);
 int ba_set_profiling(ba_handle* h, int enable);
 /* Whole-region device timing with CUDA events recorded on the handle's own stream (the stream every
  * kernel of this handle is launched on): start, run any number of calls, stop -> elapsed ms. */
+/* Debug: 16 device cycle counters of the last dense-stage kernel (phase split; see csrc/ba_dense.cuh). */
+int ba_debug_counters(ba_handle* h, long long* out16);
 int ba_timer_start(ba_handle* h);
 int ba_timer_stop(ba_handle* h, double* elapsed_ms);
 

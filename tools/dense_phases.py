@@ -1,0 +1,12 @@
+import sys; sys.path.insert(0, ".")
+from bundleadjustment_benchmarks_b200 import bal, solver
+p = bal.load_named("synthetic-5m")
+s = solver.GpuSolver(p, "QRCHOL")
+e, cn2, cn = s.linearize()
+for _ in range(3):
+    s.compute(1e-12 * cn2); s.solve_try(); s.reject()
+c = s.debug_counters()
+names = ["factor32", "trsm", "sync1", "update", "sync2", "backward(total)"]
+nt = (9 * p.N + 31) // 32
+for n, v in zip(names, c):
+    print(f"{n:16s} {v:12d} cycles  = {v/1.9e3:9.1f} us total, {v/1.9e3/nt:6.2f} us/panel")
