@@ -216,238 +216,661 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_band_ldlt_solve(BandMat<T> A,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cluster-resident variant: ONE thread-block cluster (8 portable / 16 CTAs) factors the band matrix.
-// The per-panel work of a banded factorisation is tiny (<= bt(bt+1)/2 32^3 tile updates), so the
-// chain of n/32 dependent panels is latency-bound: cluster barriers (~0.2 us) replace grid-wide
-// barriers (~4 us), the forward substitution L z = g rides along inside the factorisation (the
-// right-hand side is one more row of the matrix), W_k = L_kk^-1 is produced by the same 32
-// elimination steps as the tile factor and kept for the backward pass, which CTA 0 runs alone.
+// Cluster-resident variant (v2): ONE thread-block cluster (16 CTAs, 8 portable) factors the band
+// matrix AND solves. The per-panel work of a banded factorisation is small (<= bt(bt+1)/2 32^3 tile
+// updates), so the chain of n/32 dependent panels is latency-bound; the design removes every
+// avoidable latency from that chain (measured constants: tools/ubench, profiles/):
+//   * diagonal tile: ONE warp per CTA (redundantly, so no broadcast is needed) eliminates the
+//     32x32 tile in registers, lane = row; per step the pivot travels by warp shuffle (it feeds
+//     the 71-cycle FP64 reciprocal, the critical chain) and the pivot column by one shared-memory
+//     round trip (vector broadcast loads); no block barriers inside the 32 steps; the right-hand
+//     side rides along as a 33rd column (forward substitution L z = g).
+//   * row tiles below (L_ik = A_ik L_kk^-T D^-1): one warp per tile, lane = row, forward
+//     substitution in registers against L_kk^T broadcast from shared memory; the rows are
+//     prefetched into registers while the diagonal tile is being factored. W_k = L_kk^-1 (for the
+//     backward pass) is the same substitution applied to identity rows.
+//   * trailing update A_ij -= L_ik D_k L_jk^T: FP64 tensor cores (mma.sync m8n8k4 = DMMA), four
+//     warps per 32x32 tile, operands staged global->shared with cp.async (double-buffered, no
+//     registers), stride-36 rows -> conflict-free fragment loads, C fragments straight from/to L2.
+//   * cluster barriers (~0.2 us) instead of grid-wide barriers (~4 us).
+//   * backward pass on the whole cluster: per step the far tiles (i >= k+2) are reduced one step
+//     ahead by all CTAs into CTA 0's shared memory through DSMEM; the critical chain (CTA 0, warp 0)
+//     is two 32x32 mat-vecs: the (k+1,k) tile with y_{k+1}, then W_k^T.
+// Code size matters: the steady-state loop must stay inside the instruction cache (straight-line
+// code beyond ~128 KB runs 3x slower, tools/ubench), hence vector loads and shared helpers.
 // ---------------------------------------------------------------------------------------------
-constexpr int CL_THREADS = 512;
-constexpr int CL_GROUPS = CL_THREADS / 128;
+// Masked tile elements are loaded from this zero word (address select instead of value select): a value
+// select right after each load makes ptxas serialise load -> select -> load at the 310-cycle L2 latency.
+__device__ double ba_zero_word[2];
 
-template <class T> struct ClusterSmem {
-  T sD[NB][NB + 1]; T sW[NB][NB + 1]; T sd[NB]; T sz[NB];
-  T gA[CL_GROUPS][NB][NB + 1]; T gB[CL_GROUPS][NB][NB + 1];
+constexpr int CL_THREADS = 256;  // 8 warps: 255 registers per thread keep the register-resident factor/substitution spill-free
+constexpr int CL_WARPS = CL_THREADS / 32;
+constexpr int CL_GROUPS = CL_THREADS / 128;
+constexpr int TS = NB + 4;
+constexpr int CL_MAX_BT = 144;  // far-tile slots of the backward pass alias the operand staging area
+
+template <class T> struct VecOf;
+template <> struct VecOf<double> { using V2 = double2; };
+template <> struct VecOf<float> { using V2 = float2; };
+
+template <class T> struct PanelSmem {
+  alignas(16) T sLT[NB][NB];      // sLT[m][c] = L_kk[c][m] (0 for c <= m)
+  alignas(16) T sCol[2][2 * NB];  // pivot column broadcast (tail zero: window positions past column 31)
+  alignas(16) T sd[NB];
+  alignas(16) T sinvd[NB];
+  alignas(16) T sz[NB];
 };
 
-__device__ __forceinline__ void group_barrier(int group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(128) : "memory"); }
+template <class T> struct ClusterSmem {
+  PanelSmem<T> pn;                // L_kk^T, D, 1/D, z of the panel being factored (chain team)
+  alignas(16) T sL[NB][NB + 2];   // staged diagonal tile
+  alignas(16) T pad_[NB];         // reads past sLT's last row (dead window positions) stay inside the struct
+  alignas(16) T sdU[2][NB];       // D of panel k (parity k&1) for the trailing updates, which lag the chain by one panel
+  alignas(16) T gA[CL_GROUPS][2][2][NB][TS];  // [team][buffer][tile of the 2x2 block] row-operand tiles
+  alignas(16) T gB[CL_GROUPS][2][2][NB][TS];  // column-operand tiles
+  alignas(16) T sLk[2][NB][NB + 1];
+  alignas(16) T sWk[2][NB][NB + 1];
+  alignas(16) T sw[2][NB];
+  int work;                       // dynamic tile-op counter of the current phase
+  int grab[CL_GROUPS][2];
+  long long tc[16];
+};
+static_assert(2 * CL_MAX_BT * NB <= 2 * 2 * 2 * CL_GROUPS * NB * TS, "backward slots must fit the staging area");
 
-// batched, unconditional tile loads: 8 independent L2 requests per lane in flight
+__device__ __forceinline__ void group_barrier(int group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(128) : "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Shared-memory vector load the compiler may not sink to its use: ptxas otherwise funnels a run of
+// independent broadcast loads through one register quad and serialises load -> FMA -> load at the
+// 30-cycle LDS latency (measured in tools/ubench2: 7.4k instead of 1.2k cycles per 32x32 substitution).
+__device__ __forceinline__ double2 lds_v2(const double* p) {
+  double2 v; const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_v2(const float* p) {
+  float2 v; const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+
 template <class T>
-__device__ __forceinline__ void tile_fetch(const BandMat<T>& A, int row0, int col0, int gt, T (&reg)[8]) {
+__device__ __forceinline__ T dep0(T x, T last) { return fma(last, T(0), x); }
+
+// Reciprocal of a normal-range pivot: MUFU.RCP64H seed (~20 bits) + one cubic correction (3 dependent
+// FMAs instead of the 5 + range checks of the IEEE division): relative error ~2^-60, not correctly rounded.
+__device__ __forceinline__ double pivot_rcp(double d) {
+  double x0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(d));
+  const double e = fma(-d, x0, 1.0);
+  const double p = fma(e, e, e);
+  return fma(x0, p, x0);
+}
+__device__ __forceinline__ float pivot_rcp(float d) { return 1.0f / d; }
+
+// ---- register-resident 32x32 kernels of the panel chain --------------------------------------------
+// Both are ROLLED loops over blocks of 4 columns with the lane's row window rotated by 4 registers per
+// block, so that all register indices are static while the code stays a few KB: the fully unrolled
+// forms (45 KB + 32 KB) pushed the panel loop past the instruction cache and ran 9x slower inside the
+// kernel than in isolation (tools/ubench2, profiles/r01_dense_notes.md). Window width 32 for the first
+// 16 columns, 16 for the rest.
+
+// 4 elimination steps of the LDL^T, lane = row, a[p] = A(row, jb + p). Critical chain per step: first
+// update of the next column (9 cycles) -> pivot shuffle (30) -> reciprocal (~55) -> multiplier (9).
+// The pivot column travels by one shared-memory round trip issued as ONE batch of broadcast vector loads
+// (`dep0` ties the bulk FMAs to the last load, otherwise ptxas serialises load/FMA pairs through one
+// register); the bulk of step j is issued after step j+1's shuffles (shfl.sync is a code-motion barrier).
+template <class T, int W>
+__device__ __forceinline__ void ldlt_block4(T (&a)[NB], T& z, T& dj, T& zj, const int lane, const int jb, PanelSmem<T>& sm) {
+  using V2 = typename VecOf<T>::V2;
+  constexpr unsigned FULL = 0xffffffffu;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int idx = gt + 128 * q, r = idx >> 5, c = idx & 31, gi = row0 + r, gj = col0 + c;
-    const bool ok = band_ok(A, gi, gj);
-    const T* p = ok ? (A.v + (size_t)gi * A.lds + gj) : A.v;
-    const T v = *p;
-    reg[q] = ok ? v : T(0);
+  for (int s = 0; s < 4; ++s) {
+    const int j = jb + s;
+    const T* col = sm.sCol[s & 1];
+    V2 t[W / 2];
+#pragma unroll
+    for (int h = 0; h < W / 2; ++h)
+      if (2 * h + 1 > s) t[h] = lds_v2(col + jb + 2 * h);  // A(jb+2h, j), A(jb+2h+1, j), un-scaled
+    const T inv = pivot_rcp(dj);
+    const T l = a[s] * inv;
+    if (lane > j) z -= l * zj;
+    sm.sLT[j][lane] = (lane > j) ? l : T(0);
+    if (lane == j) { sm.sd[j] = dj; sm.sinvd[j] = inv; sm.sz[j] = zj; }
+    // column j+1 first, handed to step j+1 before the bulk of step j
+    a[s + 1] -= l * (((s + 1) & 1) ? t[(s + 1) / 2].y : t[(s + 1) / 2].x);
+    sm.sCol[(s + 1) & 1][lane] = a[s + 1];
+    dj = __shfl_sync(FULL, a[s + 1], (j + 1) & 31);
+    zj = __shfl_sync(FULL, z, (j + 1) & 31);
+    __syncwarp();
+    const T ld = dep0(l, t[W / 2 - 1].y);
+#pragma unroll
+    for (int h = 0; h < W / 2; ++h) {
+      if (2 * h > s + 1) a[2 * h] -= ld * t[h].x;
+      if (2 * h + 1 > s + 1) a[2 * h + 1] -= ld * t[h].y;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NB; ++p) a[p] = (p + 4 < W) ? a[p + 4] : T(0);
+}
+
+// lane = row, a[c] = A(row, c) for c <= row (zero above). Results go to shared memory: sLT, sd, sinvd and
+// sz = L^-1 (incoming sz).
+template <class T>
+__device__ __forceinline__ void warp_ldlt32(T (&a)[NB], T z, const int lane, PanelSmem<T>& sm) {
+  constexpr unsigned FULL = 0xffffffffu;
+  sm.sCol[0][lane] = a[0];
+  T dj = __shfl_sync(FULL, a[0], 0);
+  T zj = __shfl_sync(FULL, z, 0);
+  __syncwarp();
+#pragma unroll 1
+  for (int jb = 0; jb < NB / 2; jb += 4) ldlt_block4<T, NB>(a, z, dj, zj, lane, jb, sm);
+#pragma unroll 1
+  for (int jb = NB / 2; jb < NB; jb += 4) ldlt_block4<T, NB / 2>(a, z, dj, zj, lane, jb, sm);
+}
+
+// 4 columns of the substitution X L^T = A, lane = row, a[p] = A(row, jb + p). x_m (scaled by 1/d_m when
+// `scale`) is written to out[m * ostride] for m >= mmin; dot accumulates sum_m l_m z_m.
+template <class T, int W>
+__device__ __forceinline__ void trsm_block4(T (&a)[NB], const int jb, const PanelSmem<T>& sm, T& dot, T* __restrict__ out, const int ostride,
+                                            const bool scale, const int mmin) {
+  using V2 = typename VecOf<T>::V2;
+  V2 t[2][W / 2];
+#pragma unroll
+  for (int h = 0; h < W / 2; ++h) t[0][h] = lds_v2(&sm.sLT[jb][jb + 2 * h]);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int m = jb + s;
+    if (s + 1 < 4) {
+#pragma unroll
+      for (int h = 0; h < W / 2; ++h)
+        if (2 * h + 1 > s + 1) t[(s + 1) & 1][h] = lds_v2(&sm.sLT[m + 1][jb + 2 * h]);
+    }
+    const T xm = dep0(a[s], t[s & 1][W / 2 - 1].y);
+#pragma unroll
+    for (int h = 0; h < W / 2; ++h) {
+      if (2 * h > s) a[2 * h] -= xm * t[s & 1][h].x;
+      if (2 * h + 1 > s) a[2 * h + 1] -= xm * t[s & 1][h].y;
+    }
+    const T l = scale ? xm * sm.sinvd[m] : xm;
+    dot += l * sm.sz[m];
+    if (m >= mmin) out[(size_t)m * ostride] = l;
+  }
+#pragma unroll
+  for (int p = 0; p < NB; ++p) a[p] = (p + 4 < W) ? a[p + 4] : T(0);
+}
+
+template <class T>
+__device__ __forceinline__ T warp_trsm32(T (&a)[NB], const PanelSmem<T>& sm, T* __restrict__ out, const int ostride, const bool scale, const int mmin) {
+  T dot = T(0);
+#pragma unroll 1
+  for (int jb = 0; jb < NB / 2; jb += 4) trsm_block4<T, NB>(a, jb, sm, dot, out, ostride, scale, mmin);
+#pragma unroll 1
+  for (int jb = NB / 2; jb < NB; jb += 4) trsm_block4<T, NB / 2>(a, jb, sm, dot, out, ostride, scale, mmin);
+  return dot;
+}
+
+// acc0/acc1 (fragment layout, even/odd k-steps) += sA * (-D sB)^T over the 32-wide panel. All 40 fragment
+// loads are issued as one batch (volatile asm keeps them ahead of the DMMAs, which are volatile asm too);
+// two accumulator sets keep 8 independent DMMA chains in flight per warp (16 issue cycles each).
+__device__ __forceinline__ double lds_f64(const double* p) {
+  double v; const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void tile_mma(const double (&sA)[NB][TS], const double (&sB)[NB][TS], const double* sd, int gt, double (&acc)[8]) {
+  const int w4 = (gt >> 5) & 3, lane = gt & 31, lr = lane >> 2, lc = lane & 3;
+  const int ra = (w4 >> 1) * 16 + lr, rb = (w4 & 1) * 16 + lr;
+  double a0[NB / 4], a1[NB / 4], b0[NB / 4], b1[NB / 4], nd[NB / 4];
+#pragma unroll
+  for (int kk = 0; kk < NB / 4; ++kk) {
+    a0[kk] = lds_f64(&sA[ra][kk * 4 + lc]); a1[kk] = lds_f64(&sA[ra + 8][kk * 4 + lc]);
+    b0[kk] = lds_f64(&sB[rb][kk * 4 + lc]); b1[kk] = lds_f64(&sB[rb + 8][kk * 4 + lc]);
+    nd[kk] = lds_f64(sd + kk * 4 + lc);
+  }
+  double accb[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) accb[e] = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < NB / 4; ++kk) {
+    const double m = -nd[kk];
+    const double p0 = b0[kk] * m, p1 = b1[kk] * m;
+    if (kk & 1) {
+      dmma884(accb[0], accb[1], a0[kk], p0); dmma884(accb[2], accb[3], a0[kk], p1);
+      dmma884(accb[4], accb[5], a1[kk], p0); dmma884(accb[6], accb[7], a1[kk], p1);
+    } else {
+      dmma884(acc[0], acc[1], a0[kk], p0); dmma884(acc[2], acc[3], a0[kk], p1);
+      dmma884(acc[4], acc[5], a1[kk], p0); dmma884(acc[6], acc[7], a1[kk], p1);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] += accb[e];
+}
+__device__ __forceinline__ void tile_mma(const float (&sA)[NB][TS], const float (&sB)[NB][TS], const float* sd, int gt, float (&acc)[8]) {
+  const int c = gt & 31, r0 = (gt >> 5) & 3;
+#pragma unroll 8
+  for (int m = 0; m < NB; ++m) {
+    const float b = -sB[c][m] * sd[m];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] += sA[r0 + 4 * q][m] * b;
   }
 }
-template <class T>
-__device__ __forceinline__ void tile_stage(T (&dst)[NB][NB + 1], int gt, const T (&reg)[8]) {
+
+// One warp = one 32x32 tile of a 2x2 block: acc (16 m8n8 sub-tiles, e = 2 (4 mi + ni) + h) += sA (-D sB)^T.
+// Per k-step 8 fragment loads feed 16 independent DMMAs (16 accumulator chains hide the DMMA latency).
+__device__ __forceinline__ void block_mma(const double (&sA)[NB][TS], const double (&sB)[NB][TS], const double* sd, int lane, double (&acc)[32]) {
+  const int lr = lane >> 2, lc = lane & 3;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) { const int idx = gt + 128 * q; dst[idx >> 5][idx & 31] = reg[q]; }
+  for (int kk = 0; kk < NB / 4; ++kk) {
+    const double m = -sd[kk * 4 + lc];
+    double af[4], bf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { af[i] = sA[i * 8 + lr][kk * 4 + lc]; bf[i] = sB[i * 8 + lr][kk * 4 + lc] * m; }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) dmma884(acc[2 * (4 * mi + ni)], acc[2 * (4 * mi + ni) + 1], af[mi], bf[ni]);
+  }
+}
+__device__ __forceinline__ void block_mma(const float (&sA)[NB][TS], const float (&sB)[NB][TS], const float* sd, int lane, float (&acc)[32]) {
+  // float build: plain FMAs in the same fragment layout (row = 8 mi + lane/4, col = 8 ni + 2 (lane%4) + h)
+  const int lr = lane >> 2, lc = lane & 3;
+#pragma unroll 4
+  for (int m = 0; m < NB; ++m) {
+    const float d = -sd[m];
+    float af[4], bf[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { af[i] = sA[i * 8 + lr][m]; bf[2 * i] = sB[i * 8 + 2 * lc][m] * d; bf[2 * i + 1] = sB[i * 8 + 2 * lc + 1][m] * d; }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) { acc[2 * (4 * mi + ni)] += af[mi] * bf[2 * ni]; acc[2 * (4 * mi + ni) + 1] += af[mi] * bf[2 * ni + 1]; }
+  }
 }
 
+// element e (0..7) of a thread's C fragment -> tile-local (row, col). double: m8n8k4 accumulator
+// layout of the warp's 16x16 quadrant (e = 4 mi + 2 ni + h); float: plain 4 x 32 thread grid.
 template <class T>
-__global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> A, T* __restrict__ dvec, T* __restrict__ Wbuf,
-                                                                      T* __restrict__ rhs, T* __restrict__ y, T sign, int* __restrict__ info, long long* __restrict__ dbg) {
+__device__ __forceinline__ void frag_rc(int gt, int e, int& r, int& c) {
+  if (sizeof(T) == 8) {
+    const int w4 = (gt >> 5) & 3, lane = gt & 31;
+    r = (w4 >> 1) * 16 + (e >> 2) * 8 + (lane >> 2);
+    c = (w4 & 1) * 16 + ((e >> 1) & 1) * 8 + 2 * (lane & 3) + (e & 1);
+  } else {
+    r = ((gt >> 5) & 3) + 4 * e;
+    c = gt & 31;
+  }
+}
+
+// Kernel. Two teams of 4 warps per CTA:
+//   chain team (warps 0-3): per panel k stages the diagonal tile, warp 0 factors it (every CTA redundantly),
+//     warps 1-3 solve the CTA's row tiles (and form W_k); then joins the update team.
+//   update team (warps 4-7): 32x32 tile updates on the FP64 tensor cores.
+// Per panel two phases separated by cluster barriers (look-ahead of one panel):
+//   phase B(k): the column-(k+1) tiles receive panel k's update (all teams, <= 2 tile-ops per CTA);
+//   phase A(k+1): chain(k+1) runs while the remaining tiles (columns >= k+2) receive panel k's update;
+//     tile-ops of a phase are handed out per CTA through a shared-memory counter, so the chain team picks
+//     up whatever is left when it is done.
+template <class T>
+__global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> A, T* __restrict__ dvec, T* Wbuf,
+                                                                      T* rhs, T* y, T sign, int* __restrict__ info, long long* __restrict__ dbg) {
+  using V2 = typename VecOf<T>::V2;
   cg::cluster_group cluster = cg::this_cluster();
-  long long tc[6] = {0, 0, 0, 0, 0, 0}; long long t0 = clock64();
-#define TICK(i) { const long long t1_ = clock64(); tc[i] += t1_ - t0; t0 = t1_; }
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int EPC = 16 / (int)sizeof(T);   // elements per 16-byte chunk
+  constexpr int CPR = NB / EPC;              // chunks per tile row
+  constexpr int NCP = NB * CPR / 128;        // cp.async per thread per tile
   const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   extern __shared__ __align__(16) unsigned char cl_smem_raw[];
   ClusterSmem<T>& sm = *reinterpret_cast<ClusterSmem<T>*>(cl_smem_raw);
-  T(&sD)[NB][NB + 1] = sm.sD;
-  T(&sW)[NB][NB + 1] = sm.sW;
-  T(&sd)[NB] = sm.sd;
-  T(&sz)[NB] = sm.sz;
-  T(&gA)[CL_GROUPS][NB][NB + 1] = sm.gA;
-  T(&gB)[CL_GROUPS][NB][NB + 1] = sm.gB;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, group = warp >> 2, gt = tid & 127;
-  const int n = A.n, kd = A.kd;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, team = warp >> 2, gt = tid & 127, tw = warp & 3;
+  const int n = A.n, kd = A.kd, lds = (int)A.lds;
+  T* const Av = A.v;
+  const T* const zp = reinterpret_cast<const T*>(ba_zero_word);
   const int nt = (n + NB - 1) / NB, bt = (kd + NB - 1) / NB;
-  const int gstride = CL_GROUPS * C, gfirst = rank * CL_GROUPS + group;
-  for (int k = 0; k < nt; ++k) {
-    const int k0 = k * NB;
-    const int last = min(nt - 1, k + bt);
-    // prefetch this group's first row tile of the panel while the diagonal tile is being factored
-    T ra[8], rb[8], rc[8];
-    int it = k + 1 + gfirst;
-    if (it <= last) tile_fetch<T>(A, it * NB, k0, gt, ra);
-    for (int idx = tid; idx < NB * NB; idx += CL_THREADS) {
+  long long t0 = clock64();
+  if (tid < 16) sm.tc[tid] = 0;
+  if (tid < 2 * NB) { sm.pn.sCol[0][NB + (tid & 31)] = T(0); sm.pn.sCol[1][NB + (tid & 31)] = T(0); }
+  if (tid == 0) sm.work = 0;
+#ifdef BA_DENSE_TICKS
+#define TICK(i) { if (threadIdx.x == 128) { const long long t1_ = clock64(); sm.tc[i] += t1_ - t0; t0 = t1_; } __syncwarp(); }
+#else
+#define TICK(i) {}
+#endif
+  // per-thread constants of the tile-op path
+  int aoff[NCP], soff[NCP];
+#pragma unroll
+  for (int q = 0; q < NCP; ++q) { const int id = gt + 128 * q, r = id / CPR, ch = id % CPR; aoff[q] = r * lds + ch * EPC; soff[q] = r * TS + ch * EPC; }
+  int coff[4];
+#pragma unroll
+  for (int e = 0; e < 8; e += 2) { int r, c; frag_rc<T>(gt, e, r, c); coff[e >> 1] = r * lds + c; }
+
+  // ---- one panel of the chain: diagonal tile + row tiles of panel k (chain team only; team barriers)
+  auto chain = [&](const int k) {
+    const int k0 = k * NB, last = min(nt - 1, k + bt);
+    for (int idx = gt; idx < NB * NB; idx += 128) {
       const int r = idx >> 5, c = idx & 31, gi = k0 + r, gj = k0 + c;
-      sD[r][c] = (gi < n) ? (band_ok(A, gi, gj) ? A.v[(size_t)gi * A.lds + gj] : T(0)) : (r == c ? T(1) : T(0));
-      sW[r][c] = (r == c) ? T(1) : T(0);
+      const bool ok = gi < n && c <= r && gi - gj <= kd;
+      const T v = *(ok ? Av + (size_t)gi * lds + gj : zp);
+      sm.sL[r][c] = (gi >= n && r == c) ? T(1) : v;
     }
-    if (tid < NB) sz[tid] = (k0 + tid < n) ? rhs[k0 + tid] : T(0);
-    // 32 elimination steps on [A_kk | I | g_k]: A_kk -> L D (column scaling deferred), I -> L^-1, g_k -> z_k
-    for (int j = 0; j < NB; ++j) {
-      __syncthreads();
-      const T inv = T(1) / sD[j][j];
-      for (int idx = tid; idx < NB * NB; idx += CL_THREADS) {
-        const int i = idx >> 5, c = idx & 31;
-        if (i > j) {
-          const T l = sD[i][j] * inv;
-          if (c > j) { if (c <= i) sD[i][c] -= l * sD[c][j]; }
-          else sW[i][c] -= l * sW[j][c];
+    if (gt < NB) sm.pn.sz[gt] = *((k0 + gt < n) ? rhs + k0 + gt : zp);
+    // row-tile warps prefetch their rows (lane = row) while the diagonal tile is factored. Work items of
+    // warps 1..3: the CTA's row tiles it = k+1+rank+C*u; warp 3 of CTA k%C first forms W_k (identity rows).
+    T a[NB];
+    const bool w_warp = (tw == 3) && (rank == k % C);
+    int it = k + 1 + rank + C * (tw - 1);
+    bool pre = (tw >= 1) && !w_warp && (it <= last);
+    if (pre) {
+      const int gi = it * NB + lane;
+      const T* rp = Av + (size_t)gi * lds + k0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) { const bool ok = gi < n && gi - (k0 + c) <= kd; a[c] = *(ok ? rp + c : zp); }
+    }
+    group_barrier(0);
+    if (tw == 0) {
+      const T z = sm.pn.sz[lane];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) a[c] = (c <= lane) ? sm.sL[lane][c] : T(0);
+      warp_ldlt32<T>(a, z, lane, sm.pn);
+      __syncwarp();
+      const T d = sm.pn.sd[lane];
+      sm.sdU[k & 1][lane] = d;
+      if (rank == 0 && k0 + lane < n && (d == T(0) || !(d == d))) atomicCAS(info, 0, k0 + lane + 1);
+    }
+    group_barrier(0);
+    if (tw >= 1) {
+      bool do_w = w_warp;
+      while (do_w || it <= last) {
+        const int gi = it * NB + lane;
+        if (do_w) {
+#pragma unroll
+          for (int c = 0; c < NB; ++c) a[c] = (c == lane) ? T(1) : T(0);
+        } else if (!pre) {
+          const T* rp = Av + (size_t)gi * lds + k0;
+#pragma unroll
+          for (int c = 0; c < NB; ++c) { const bool ok = gi < n && gi - (k0 + c) <= kd; a[c] = *(ok ? rp + c : zp); }
+        }
+        pre = false;
+        // one substitution call site (code size): W mode = identity rows, x[c] = W(c, lane), un-scaled;
+        // tile mode = X L_kk^T = A_ik, L_ik = X D^-1, g_i -= L_ik z_k
+        T* out = do_w ? (Wbuf + (size_t)k * NB * NB + lane) : (Av + (size_t)gi * lds + k0);
+        const int ostride = do_w ? NB : 1;
+        const int mmin = do_w ? 0 : ((gi < n) ? max(0, gi - k0 - kd) : NB);
+        const T s = warp_trsm32<T>(a, sm.pn, out, ostride, !do_w, mmin);
+        if (do_w) do_w = false;
+        else {
+          if (gi < n) rhs[gi] = rhs[gi] - s;
+          it += C * 3;
         }
       }
-      if (tid < NB && tid > j) sz[tid] -= sD[tid][j] * inv * sz[j];
     }
-    __syncthreads();
-    if (tid < NB) {
-      const T d = sD[tid][tid];
-      sd[tid] = d;
-      if (rank == 0 && k0 + tid < n && (d == T(0) || !(d == d))) atomicCAS(info, 0, k0 + tid + 1);
-    }
-    __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += CL_THREADS) { const int r = idx >> 5, c = idx & 31; if (c < r) sD[r][c] = sD[r][c] / sd[c]; }
-    TICK(0)
-    // row tiles below: L_ik = A_ik W^T D^-1 ; forward substitution g_i -= L_ik z_k
-    for (; it <= last; it += gstride) {
-      tile_stage<T>(gA[group], gt, ra);
-      group_barrier(group);
-      if (it + gstride <= last) tile_fetch<T>(A, (it + gstride) * NB, k0, gt, ra);
-      const int c = gt & 31, rb8 = (gt >> 5) * 8;
-      T acc[8] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
-#pragma unroll 4
-      for (int m = 0; m < NB; ++m) {
-        const T w = sW[c][m];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] += gA[group][rb8 + q][m] * w;
-      }
-      const T idc = T(1) / sd[c];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int gi = it * NB + rb8 + q, gj = k0 + c;
-        const bool ok = band_ok(A, gi, gj);
-        const T v = ok ? acc[q] * idc : T(0);
-        gB[group][rb8 + q][c] = v;
-        if (ok) A.v[(size_t)gi * A.lds + gj] = v;
-      }
-      group_barrier(group);
-      if (gt < NB) {
-        const int gi = it * NB + gt;
-        if (gi < n) {
-          T s = T(0);
-#pragma unroll 8
-          for (int cc = 0; cc < NB; ++cc) s += gB[group][gt][cc] * sz[cc];
-          rhs[gi] -= s;
-        }
-      }
-      group_barrier(group);
-    }
-    TICK(1)
-    cluster.sync();
-    TICK(2)
-    // trailing update A_ij -= L_ik D_k L_jk^T, k < j <= i <= last; operands one tile ahead in registers
-    const int nb = last - k;
-    const int npairs = nb * (nb + 1) / 2;
-    auto decode = [&](int pidx, int& ti, int& tj) {
-      int ii = (int)((sqrtf(8.0f * (float)pidx + 1.0f) - 1.0f) * 0.5f);
-      while ((ii + 1) * (ii + 2) / 2 <= pidx) ++ii;
-      while (ii * (ii + 1) / 2 > pidx) --ii;
-      ti = k + 1 + ii; tj = k + 1 + (pidx - ii * (ii + 1) / 2);
-    };
-    int pidx = gfirst, ti = 0, tj = 0;
-    if (pidx < npairs) { decode(pidx, ti, tj); tile_fetch<T>(A, ti * NB, k0, gt, ra); tile_fetch<T>(A, tj * NB, k0, gt, rb); tile_fetch<T>(A, ti * NB, tj * NB, gt, rc); }
-    if (rank == 0) {  // publish the factored diagonal tile, D, W_k and w_k = D^-1 z_k (overlaps the fetch latency)
-      for (int idx = tid; idx < NB * NB; idx += CL_THREADS) {
+    if (rank == 0) {  // publish the factored diagonal tile, D and w_k = D^-1 z_k
+      for (int idx = gt; idx < NB * NB; idx += 128) {
         const int r = idx >> 5, c = idx & 31, gi = k0 + r, gj = k0 + c;
-        if (band_ok(A, gi, gj)) A.v[(size_t)gi * A.lds + gj] = (r == c) ? sd[c] : sD[r][c];
-        Wbuf[(size_t)k * NB * NB + idx] = sW[r][c];
+        if (gi < n && gj <= gi && gi - gj <= kd) Av[(size_t)gi * lds + gj] = (r == c) ? sm.pn.sd[c] : sm.pn.sLT[c][r];
       }
-      if (tid < NB && k0 + tid < n) { dvec[k0 + tid] = sd[tid]; rhs[k0 + tid] = sz[tid] / sd[tid]; }
+      if (gt < NB && k0 + gt < n) { dvec[k0 + gt] = sm.pn.sd[gt]; rhs[k0 + gt] = sm.pn.sz[gt] * sm.pn.sinvd[gt]; }
     }
-    for (; pidx < npairs; pidx += gstride) {
-      const int ci = ti, cj = tj;
-      tile_stage<T>(gA[group], gt, ra);
+    group_barrier(0);  // everyone is done with pn before the next chain() overwrites it
+  };
+
+  // ---- tile (t, k) -> shared memory
+  auto stage_operand = [&](T (&dst)[NB][TS], const int t, const int k0) {
+    const int row0 = t * NB;
+    const bool interior = (row0 + NB - 1 < n) && (row0 + NB - 1 - k0 <= kd);
+    const T* tp = Av + (size_t)row0 * lds + k0;
+    if (interior) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { const int idx = gt + 128 * q; gB[group][idx >> 5][idx & 31] = rb[q] * sd[idx & 31]; }
-      T cc[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) cc[q] = rc[q];
-      group_barrier(group);
-      if (pidx + gstride < npairs) { decode(pidx + gstride, ti, tj); tile_fetch<T>(A, ti * NB, k0, gt, ra); tile_fetch<T>(A, tj * NB, k0, gt, rb); tile_fetch<T>(A, ti * NB, tj * NB, gt, rc); }
-      // lane layout of the fetch: element idx = gt + 128 q -> row (idx>>5), col (idx&31): compute the same elements
-      T acc[8] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
-      const int c = gt & 31, r0 = gt >> 5;  // rows r0, r0+4, ..., r0+28
-#pragma unroll 4
-      for (int m = 0; m < NB; ++m) {
-        const T b = gB[group][c][m];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] += gA[group][r0 + 4 * q][m] * b;
-      }
+      for (int q = 0; q < NCP; ++q) cp_async16(&dst[0][0] + soff[q], tp + aoff[q]);
+    } else {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int gi = ci * NB + r0 + 4 * q, gj = cj * NB + c;
-        if (band_ok(A, gi, gj)) A.v[(size_t)gi * A.lds + gj] = cc[q] - acc[q];
+        const int idx = gt + 128 * q, r = idx >> 5, c = idx & 31, gi = row0 + r;
+        const bool ok = gi < n && gi - (k0 + c) <= kd;
+        dst[r][c] = *(ok ? tp + r * lds + c : zp);
       }
-      group_barrier(group);
     }
+  };
+  // ---- a phase of tile updates with panel k: items p = rank + C*t handed out through sm.work.
+  // col_phase: tiles (k+1+p, k+1); otherwise tiles (i, j), k+2 <= j <= i <= last, p = ii(ii+1)/2 + jj.
+  auto tile_phase = [&](const int k, const bool col_phase) {
+    const int k0 = k * NB, last = min(nt - 1, k + bt), nb = last - k;
+    const int count = col_phase ? nb : (nb - 1) * nb / 2;
+    const T* sd = sm.sdU[k & 1];
+    auto decode = [&](int p, int& ti, int& tj) {
+      if (col_phase) { ti = k + 1 + p; tj = k + 1; return; }
+      int ii = (int)((__fsqrt_rn(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+      while ((ii + 1) * (ii + 2) / 2 <= p) ++ii;
+      while (ii * (ii + 1) / 2 > p) --ii;
+      ti = k + 2 + ii; tj = k + 2 + (p - ii * (ii + 1) / 2);
+    };
+    int slot = 0, buf = 0, ti = 0, tj = 0;
+    if (gt == 0) sm.grab[team][0] = atomicAdd(&sm.work, 1);
+    group_barrier(team);
+    int p = rank + C * sm.grab[team][0];
+    if (p < count) { decode(p, ti, tj); stage_operand(sm.gA[team][0][0], ti, k0); stage_operand(sm.gB[team][0][0], tj, k0); cp_async_commit(); }
+    while (p < count) {
+      const int ci = ti, cj = tj;
+      slot ^= 1;
+      if (gt == 0) sm.grab[team][slot] = atomicAdd(&sm.work, 1);
+      cp_async_wait_all();
+      group_barrier(team);  // operands landed; next item visible; everyone is done with the other buffer
+      p = rank + C * sm.grab[team][slot];
+      if (p < count) { decode(p, ti, tj); stage_operand(sm.gA[team][buf ^ 1][0], ti, k0); stage_operand(sm.gB[team][buf ^ 1][0], tj, k0); cp_async_commit(); }
+      T* cp = Av + (size_t)(ci * NB) * lds + cj * NB;
+      const bool interior = (ci != cj) && (ci * NB + NB - 1 < n) && (ci * NB + NB - 1 - cj * NB <= kd);
+      T cc[8], acc[8];
+      if (sizeof(T) == 8 && interior) {
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) { const V2 v = *reinterpret_cast<const V2*>(cp + coff[e >> 1]); cc[e] = v.x; cc[e + 1] = v.y; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          int r, c; frag_rc<T>(gt, e, r, c);
+          const int gi = ci * NB + r, gj = cj * NB + c;
+          const bool ok = gi < n && gj <= gi && gi - gj <= kd;
+          cc[e] = *(ok ? cp + r * lds + c : zp);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = T(0);
+      tile_mma(sm.gA[team][buf][0], sm.gB[team][buf][0], sd, gt, acc);
+      if (sizeof(T) == 8 && interior) {
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) { V2 v; v.x = cc[e] + acc[e]; v.y = cc[e + 1] + acc[e + 1]; *reinterpret_cast<V2*>(cp + coff[e >> 1]) = v; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          int r, c; frag_rc<T>(gt, e, r, c);
+          const int gi = ci * NB + r, gj = cj * NB + c;
+          if (gi < n && gj <= gi && gi - gj <= kd) cp[r * lds + c] = cc[e] + acc[e];
+        }
+      }
+      buf ^= 1;
+    }
+  };
+
+  // ---- the remaining tiles (columns >= k+2) receive panel k's update in 2x2 blocks of tiles: block (I, J),
+  // J <= I, covers tile rows k+2+2I(+1) and tile columns k+2+2J(+1); each warp of the team owns one of the
+  // four 32x32 tiles (skipped when above the diagonal, past the last row tile, or outside the band); the four
+  // operand tiles are staged once per block with cp.async (double-buffered). Items p = rank + C*t.
+  auto block_phase = [&](const int k) {
+    const int k0 = k * NB, last = min(nt - 1, k + bt), nb = last - k;
+    const int nbk = nb / 2;  // ceil((nb - 1) / 2) block rows
+    const int count = nbk * (nbk + 1) / 2;
+    const T* sd = sm.sdU[k & 1];
+    auto decode = [&](int p, int& bi, int& bj) {
+      int ii = (int)((__fsqrt_rn(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+      while ((ii + 1) * (ii + 2) / 2 <= p) ++ii;
+      while (ii * (ii + 1) / 2 > p) --ii;
+      bi = ii; bj = p - ii * (ii + 1) / 2;
+    };
+    auto stage_block = [&](const int b, const int bi, const int bj) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ta = k + 2 + 2 * bi + h, tb = k + 2 + 2 * bj + h;
+        if (ta <= last) stage_operand(sm.gA[team][b][h], ta, k0);
+        if (tb <= last) stage_operand(sm.gB[team][b][h], tb, k0);
+      }
+      cp_async_commit();
+    };
+    int slot = 0, buf = 0, bi = 0, bj = 0;
+    if (gt == 0) sm.grab[team][0] = atomicAdd(&sm.work, 1);
+    group_barrier(team);
+    int p = rank + C * sm.grab[team][0];
+    if (p < count) { decode(p, bi, bj); stage_block(0, bi, bj); }
+    const int lr = lane >> 2, lc = lane & 3;
+    while (p < count) {
+      const int ci = k + 2 + 2 * bi + (tw >> 1), cj = k + 2 + 2 * bj + (tw & 1);  // this warp's tile
+      slot ^= 1;
+      if (gt == 0) sm.grab[team][slot] = atomicAdd(&sm.work, 1);
+      // C fragments straight into the accumulators (in flight while the operands land)
+      const bool active = ci <= last && cj <= ci && (ci - cj) * NB - (NB - 1) <= kd;
+      const bool interior = active && (ci != cj) && (ci * NB + NB - 1 < n) && (ci * NB + NB - 1 - cj * NB <= kd);
+      T* cp = Av + (size_t)(ci * NB) * lds + cj * NB;
+      T acc[32];
+      if (interior) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            const V2 v = *reinterpret_cast<const V2*>(cp + (mi * 8 + lr) * lds + ni * 8 + 2 * lc);
+            acc[2 * (4 * mi + ni)] = v.x; acc[2 * (4 * mi + ni) + 1] = v.y;
+          }
+      } else if (active) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int r = (e >> 3) * 8 + lr, c = ((e >> 1) & 3) * 8 + 2 * lc + (e & 1), gi = ci * NB + r, gj = cj * NB + c;
+          const bool ok = gi < n && gj <= gi && gi - gj <= kd;
+          acc[e] = *(ok ? cp + r * lds + c : zp);
+        }
+      }
+      cp_async_wait_all();
+      group_barrier(team);  // operands landed; next item visible; everyone is done with the other buffer
+      p = rank + C * sm.grab[team][slot];
+      if (p < count) { decode(p, bi, bj); stage_block(buf ^ 1, bi, bj); }
+      if (active) {
+        block_mma(sm.gA[team][buf][tw >> 1], sm.gB[team][buf][tw & 1], sd, lane, acc);
+        if (interior) {
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+              V2 v; v.x = acc[2 * (4 * mi + ni)]; v.y = acc[2 * (4 * mi + ni) + 1];
+              *reinterpret_cast<V2*>(cp + (mi * 8 + lr) * lds + ni * 8 + 2 * lc) = v;
+            }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int r = (e >> 3) * 8 + lr, c = ((e >> 1) & 3) * 8 + 2 * lc + (e & 1), gi = ci * NB + r, gj = cj * NB + c;
+            if (gi < n && gj <= gi && gi - gj <= kd) cp[r * lds + c] = acc[e];
+          }
+        }
+      }
+      buf ^= 1;
+    }
+  };
+
+  // ================= factorisation with one panel of look-ahead
+  __syncthreads();
+  if (team == 0) chain(0);
+  cluster.sync();
+  for (int k = 0; k < nt; ++k) {
+    tile_phase(k, true);                       // phase B(k): column k+1 <- panel k
+    __syncthreads();
+    if (tid == 0) sm.work = 0;
+    TICK(0)
+    cluster.sync();
+    TICK(1)
+    if (team == 0 && k + 1 < nt) chain(k + 1); // phase A(k+1): next panel's chain ...
+    TICK(2)
+    block_phase(k);                            // ... while columns >= k+2 <- panel k (2x2 tile blocks)
     TICK(3)
+    __syncthreads();
+    if (tid == 0) sm.work = 0;
     cluster.sync();
     TICK(4)
   }
-  if (rank != 0) return;
-  // ------------------------------------------------------------------ backward pass on CTA 0
-  // y_k = W_k^T (w_k - sum_{r > k0+31} L[r][k0+c] y[r]). Software pipeline: warps 1..15 accumulate, one
-  // step ahead, the rows that are already final (r >= k0+64); warp 0 adds the tile (k+1,k) product with
-  // the just-computed y_{k+1} and applies W_k^T. One block barrier per step.
-  T(*sacc)[NB] = reinterpret_cast<T(*)[NB]>(&gA[0][0][0]);          // [2][16][32] partial sums, double-buffered
-  T(*sLk)[NB + 1] = reinterpret_cast<T(*)[NB + 1]>(&gB[0][0][0]);   // [2][32][33] tile (k+1,k), double-buffered
-  T(*sWk)[NB + 1] = reinterpret_cast<T(*)[NB + 1]>(&gB[2][0][0]);   // [2][32][33] W_k, double-buffered
-  __shared__ T sy[2][NB];
-  constexpr int NWARP = CL_THREADS / 32;
-  auto stage = [&](int k, int buf) {  // executed by warps 1..15 for step k
-    const int k0 = k * NB, w = warp - 1;
-    T acc = T(0);
-    const int r1 = min(n - 1, k0 + NB - 1 + kd), gj = k0 + lane;
-    if (gj < n) {
-#pragma unroll 4
-      for (int r = k0 + 2 * NB + w; r <= r1; r += NWARP - 1)
-        if (r - gj <= kd) acc += A.v[(size_t)r * A.lds + gj] * y[r];
+  // ------------------------------------------------------------------ backward pass, whole cluster
+  T* slots = &sm.gA[0][0][0][0][0];                    // [2][bt][NB] far-tile partial sums, written through DSMEM
+  T* slots0 = cluster.map_shared_rank(slots, 0);    // CTA 0's copy
+  auto stage = [&](int km) {  // everything step km needs except y_{km+1}: executed one step ahead
+    const int km0 = km * NB;
+    const int nfar = min(nt - 1, km + bt) - (km + 2) + 1;
+    if (warp >= 1 && warp <= 3) {
+      for (int s = rank + C * (warp - 1); s < nfar; s += C * 3) {
+        const int i = km + 2 + s, gj = km0 + lane;
+        const T yv = *((i * NB + lane < n) ? y + i * NB + lane : zp);
+        const T* tp = Av + (size_t)(i * NB) * lds + gj;
+        T v[NB];
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+          const int g0 = i * NB + r;
+          const bool ok0 = g0 < n && gj < n && g0 - gj <= kd;
+          v[r] = *(ok0 ? tp + r * lds : zp);
+        }
+        T acc0 = T(0), acc1 = T(0);
+#pragma unroll
+        for (int r = 0; r < NB; r += 2) {
+          acc0 += v[r] * __shfl_sync(FULL, yv, r);
+          acc1 += v[r + 1] * __shfl_sync(FULL, yv, r + 1);
+        }
+        slots0[((size_t)(km & 1) * bt + s) * NB + lane] = sign * (acc0 + acc1);  // y holds sign * solution
+      }
     }
-    sacc[buf * NWARP + warp][lane] = acc;
-    for (int idx = (warp - 1) * 32 + lane; idx < NB * NB; idx += (NWARP - 1) * 32) {
-      const int r = idx >> 5, c = idx & 31, gi = k0 + NB + r, gjj = k0 + c;
-      sLk[buf * NB + r][c] = (gi < n && gjj < n && gi - gjj <= kd) ? A.v[(size_t)gi * A.lds + gjj] : T(0);
-      sWk[buf * NB + r][c] = Wbuf[(size_t)k * NB * NB + idx];
+    if (rank == 0 && warp >= 4) {
+      const int p = km & 1;
+      for (int idx = (warp - 4) * 32 + lane; idx < NB * NB; idx += 4 * 32) {
+        const int r = idx >> 5, c = idx & 31, gi = km0 + NB + r, gj = km0 + c;
+        const bool ok = gi < n && gj < n && gi - gj <= kd;
+        sm.sLk[p][r][c] = *(ok ? (Av + (size_t)gi * lds + gj) : zp);
+        sm.sWk[p][r][c] = Wbuf[(size_t)km * NB * NB + idx];
+      }
+      if (warp == 4) sm.sw[p][lane] = *((km0 + lane < n) ? rhs + km0 + lane : zp);
     }
   };
-  if (tid < NB) { sy[0][tid] = T(0); sy[1][tid] = T(0); }
-  if (warp > 0) stage(nt - 1, (nt - 1) & 1);
-  __syncthreads();
+  stage(nt - 1);
+  cluster.sync();
+  T yprev = T(0);
   for (int k = nt - 1; k >= 0; --k) {
-    const int k0 = k * NB, buf = k & 1;
-    if (warp == 0) {
-      T b = (k0 + lane < n) ? rhs[k0 + lane] : T(0);
-#pragma unroll
-      for (int w = 1; w < NWARP; ++w) b -= sacc[buf * NWARP + w][lane];
-      // tile (k+1,k): rows of tile k+1 times y_{k+1} (kept in sy[(k+1)&1])
-      T t = T(0);
+    if (rank == 0 && warp == 0) {
+      const int p = k & 1, k0 = k * NB;
+      const int nfar = min(nt - 1, k + bt) - (k + 2) + 1;
+      T b0 = sm.sw[p][lane], b1 = T(0);
+      for (int s = 0; s < nfar; ++s) b0 -= slots[((size_t)p * bt + s) * NB + lane];
+      if (k + 1 < nt) {
 #pragma unroll 8
-      for (int r = 0; r < NB; ++r) t += sLk[buf * NB + r][lane] * sy[(k + 1) & 1][r];
-      if (k + 1 < nt) b -= t;
-      T yv = T(0);
-#pragma unroll
-      for (int m = 0; m < NB; ++m) {
-        const T bm = __shfl_sync(0xffffffffu, b, m);
-        if (m >= lane) yv += sWk[buf * NB + m][lane] * bm;
+        for (int r = 0; r < NB; r += 2) {
+          b0 -= sm.sLk[p][r][lane] * __shfl_sync(FULL, yprev, r);
+          b1 -= sm.sLk[p][r + 1][lane] * __shfl_sync(FULL, yprev, r + 1);
+        }
       }
-      sy[buf][lane] = (k0 + lane < n) ? yv : T(0);
-      if (k0 + lane < n) y[k0 + lane] = yv;
+      const T b = b0 + b1;
+      T y0 = T(0), y1 = T(0);
+#pragma unroll 8
+      for (int m = 0; m < NB; m += 2) {
+        y0 += sm.sWk[p][m][lane] * __shfl_sync(FULL, b, m);
+        y1 += sm.sWk[p][m + 1][lane] * __shfl_sync(FULL, b, m + 1);
+      }
+      yprev = (k0 + lane < n) ? (y0 + y1) : T(0);
+      if (k0 + lane < n) y[k0 + lane] = sign * yprev;
     } else if (k > 0) {
-      stage(k - 1, (k - 1) & 1);  // needs y rows >= (k-1)*32+64 = k0+32: final since the previous step
+      stage(k - 1);
     }
-    __syncthreads();
+    cluster.sync();
   }
-  if (sign != T(1)) for (int i = tid; i < n; i += CL_THREADS) y[i] = sign * y[i];
   TICK(5)
-  if (dbg && tid == 0) for (int i = 0; i < 6; ++i) dbg[i] = tc[i];
+  if (dbg && rank == 0 && tid == 128) for (int i = 0; i < 16; ++i) dbg[i] = sm.tc[i];
 #undef TICK
 }
 

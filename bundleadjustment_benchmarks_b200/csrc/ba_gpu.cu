@@ -208,6 +208,7 @@ struct ba_handle {
   virtual int timer_start() = 0;
   virtual int timer_stop(double*) = 0;
   virtual int debug_counters(long long*) = 0;
+  virtual int debug_band_solve(int, int, const double*, const double*, double*) = 0;
   int bw = 0;
   bool keep_reduced = false;
   bool force_grid_ldlt = false;
@@ -221,7 +222,7 @@ namespace {
 template <class T>
 struct Impl : ba_handle {
   int N = 0, M = 0, K = 0, device = 0, variant = 0, ntiles = 0;
-  int n = 0, kd = 0;
+  int n = 0, kd = 0, ldsv = 0;  // ldsv: row stride of the band view, kd padded to 16 bytes
   T tau2 = T(0.25);
   double lambda = 0.0;
   bool computed = false, tried = false, linearized = false;
@@ -253,8 +254,9 @@ struct Impl : ba_handle {
   }
 
   T* Sraw() { return d_red.p; }
-  T* Sv() { return d_red.p + kd; }
-  size_t lds() const { return (size_t)kd; }
+  T* Sv() { return d_red.p + ldsv; }
+  size_t lds() const { return (size_t)ldsv; }
+  static int pad_lds(int kd_) { const int a = 16 / (int)sizeof(T); return (kd_ + a - 1) / a * a; }
   T* gvec() { return d_red.p + red_count; }
   BandMat<T> band() { return BandMat<T>{Sv(), lds(), n, kd}; }
   static constexpr ncclDataType_t nccl_t() { return sizeof(T) == 8 ? ncclDouble : ncclFloat; }
@@ -263,7 +265,8 @@ struct Impl : ba_handle {
     kd = std::min(9 * N - 1, 9 * bw + 8);
     if (kd < 1) kd = 1;
     n = 9 * N;
-    red_count = (size_t)n * (kd + 1);
+    ldsv = pad_lds(kd);
+    red_count = (size_t)n * (ldsv + 1);
     CK(d_red.alloc(red_count + n));
     CK(d_y.alloc(n)); CK(d_dvec.alloc(n));
     if (keep_reduced) CK(d_keep.alloc(red_count + n));
@@ -469,12 +472,23 @@ struct Impl : ba_handle {
       CK(cudaMemcpyAsync(d_keep.p, d_red.p, (red_count + n) * sizeof(T), cudaMemcpyDeviceToDevice, stream));
     }
     mark(3);
+    { int rc = factor_reduced(); if (rc) return rc; }
+    mark(4);
+    static const int stages[] = {0, 1, 2, 3};
+    collect(0, 4, stages);
+    if (!profiling) { /* stay asynchronous: errors surface in solve_try */ }
+    computed = true; tried = false;
+    return BA_OK;
+  }
+
+  // factorisation of the reduced camera block in d_red (LDL^T or Householder QR of S)
+  int factor_reduced() {
     if (variant == BA_QRCHOL || variant == BA_CHOLESKY) {
       CK(cudaMemsetAsync(d_info.p, 0, sizeof(int), stream));
       BandMat<T> A = band();
       const int nt = (n + NB - 1) / NB, bt = (kd + NB - 1) / NB;
       const double flops = (double)n * kd * kd;
-      if (flops < 2e11 && !force_grid_ldlt) {
+      if (flops < 2e11 && bt <= CL_MAX_BT && !force_grid_ldlt) {
         // latency-bound regime: one cluster, forward solve folded in, backward solve by CTA 0
         if (d_W.n < (size_t)nt * NB * NB) CK(d_W.alloc((size_t)nt * NB * NB));
         cudaLaunchConfig_t cfg = {};
@@ -498,11 +512,6 @@ struct Impl : ba_handle {
       int rc = qr_factor();
       if (rc) return rc;
     }
-    mark(4);
-    static const int stages[] = {0, 1, 2, 3};
-    collect(0, 4, stages);
-    if (!profiling) { /* stay asynchronous: errors surface in solve_try */ }
-    computed = true; tried = false;
     return BA_OK;
   }
 
@@ -522,11 +531,8 @@ struct Impl : ba_handle {
     return BA_OK;
   }
 
-  int solve_try(double* dx_norm, double* rho_den, double* energy_test) override {
-    CK(cudaSetDevice(device));
-    if (!computed) return fail(BA_ERR_STATE, "ba_solve_try called before ba_compute");
-    const T lamT = (T)lambda;
-    mark(4);
+  // dx_cam = -S^-1 g from the factor above
+  int solve_reduced() {
     if (variant == BA_QRCHOL || variant == BA_CHOLESKY) {
       // QR variants: y = S^-1 g, dx_cam = -y. CHOLESKY: g already holds b_c - W V^-1 b_p up to sign (see k_schur), same sign rule.
       if (!solved_in_factor) {
@@ -541,6 +547,15 @@ struct Impl : ba_handle {
       k_band_qr_backsolve<T><<<1, QR_SOLVE_THREADS, 0, stream>>>(Q, rhs, d_dx_cam.p, T(-1));
       launches++;
     }
+    return BA_OK;
+  }
+
+  int solve_try(double* dx_norm, double* rho_den, double* energy_test) override {
+    CK(cudaSetDevice(device));
+    if (!computed) return fail(BA_ERR_STATE, "ba_solve_try called before ba_compute");
+    const T lamT = (T)lambda;
+    mark(4);
+    { int rc = solve_reduced(); if (rc) return rc; }
     CK(cudaGetLastError());
     mark(5);
     k_cam_update<T><<<1, 1024, 0, stream>>>(N, d_cams.p, d_dx_cam.p, d_cams_test.p, d_scal.p + 4);
@@ -624,7 +639,7 @@ struct Impl : ba_handle {
     for (size_t i = 0; i < (size_t)n * n; ++i) S[i] = 0.0;
     for (int i = 0; i < n; ++i)
       for (int j = std::max(0, i - kd); j <= i; ++j) {
-        const double v = (double)tmp[(size_t)kd + (size_t)i * kd + j];
+        const double v = (double)tmp[(size_t)ldsv + (size_t)i * ldsv + j];
         S[(size_t)i * n + j] = v; S[(size_t)j * n + i] = v;
       }
     for (int i = 0; i < n; ++i) g[i] = (double)tmp[red_count + i];
@@ -662,6 +677,34 @@ struct Impl : ba_handle {
     CK(cudaSetDevice(device));
     CK(cudaMemcpy(out, d_dbg.p, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     return BA_OK;
+  }
+
+  // Test hook: factor + solve an arbitrary symmetric band system with this handle's reduced-system
+  // solver (LDLT variants: band LDL^T; QR variants: Householder QR of S). S dense row-major n x n.
+  int debug_band_solve(int n_, int kd_, const double* S, const double* g, double* yout) override {
+    CK(cudaSetDevice(device));
+    const int n0 = n, kd0 = kd, lds0 = ldsv; const size_t rc0 = red_count;
+    n = n_; kd = std::max(1, std::min(kd_, n_ - 1)); ldsv = pad_lds(kd); red_count = (size_t)n * (ldsv + 1);
+    DevBuf<T> red, yv, dv, dxc;
+    CK(red.alloc(red_count + n)); CK(yv.alloc(n)); CK(dv.alloc(n)); CK(dxc.alloc(n));
+    std::vector<T> hb(red_count + n, T(0));
+    for (int i = 0; i < n; ++i)
+      for (int j = std::max(0, i - kd); j <= i; ++j) hb[(size_t)ldsv + (size_t)i * ldsv + j] = (T)S[(size_t)i * n + j];
+    for (int i = 0; i < n; ++i) hb[red_count + i] = (T)g[i];
+    std::swap(d_red.p, red.p); std::swap(d_dvec.p, dv.p); std::swap(d_dx_cam.p, dxc.p);
+    int rc = BA_OK;
+    cudaError_t ce = cudaMemcpyAsync(d_red.p, hb.data(), hb.size() * sizeof(T), cudaMemcpyHostToDevice, stream);
+    if (ce == cudaSuccess) {
+      rc = factor_reduced();
+      if (!rc) rc = solve_reduced();
+      if (!rc) rc = d2h(d_dx_cam.p, yout, (size_t)n);
+      for (int i = 0; i < n && !rc; ++i) yout[i] = -yout[i];  // the solvers return dx_cam = -y
+    }
+    cudaStreamSynchronize(stream);
+    std::swap(d_red.p, red.p); std::swap(d_dvec.p, dv.p); std::swap(d_dx_cam.p, dxc.p);
+    n = n0; kd = kd0; ldsv = lds0; red_count = rc0; d_qr.free();
+    if (ce != cudaSuccess) return fail(BA_ERR_CUDA, "debug_band_solve upload: %s", cudaGetErrorString(ce));
+    return rc;
   }
 
   int set_bandwidth(int bw_) override {
@@ -722,6 +765,7 @@ int ba_stage_ms(ba_handle* h, double* s) { H_CHECK; for (int i = 0; i < 8; ++i) 
 int ba_set_profiling(ba_handle* h, int enable) { H_CHECK; h->profiling = enable != 0; return BA_OK; }
 int ba_debug_counters(ba_handle* h, long long* out16) { H_CHECK; return h->debug_counters(out16); }
 int ba_timer_start(ba_handle* h) { H_CHECK; return h->timer_start(); }
+int ba_debug_band_solve(ba_handle* h, int n, int kd, const double* S, const double* g, double* y) { H_CHECK; return h->debug_band_solve(n, kd, S, g, y); }
 int ba_timer_stop(ba_handle* h, double* ms) { H_CHECK; return h->timer_stop(ms); }
 
 }  // extern "C"

@@ -162,6 +162,13 @@ class GpuSolver:
         self._ck(self._L.ba_debug_counters(self._h, v))
         return list(v)
 
+    def debug_band_solve(self, S, g, kd):
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        y = np.empty(S.shape[0])
+        self._ck(self._L.ba_debug_band_solve(self._h, S.shape[0], int(kd), _dp(S), _dp(g), _dp(y)))
+        return y
+
     def timer_start(self):
         self._ck(self._L.ba_timer_start(self._h))
 

@@ -109,6 +109,9 @@ int ba_set_profiling(ba_handle* h, int enable);
  * kernel of this handle is launched on): start, run any number of calls, stop -> elapsed ms. */
 /* Debug: 16 device cycle counters of the last dense-stage kernel (phase split; see csrc/ba_dense.cuh). */
 int ba_debug_counters(ba_handle* h, long long* out16);
+/* Test hook (not on the hot path): factor + solve S y = g for an arbitrary symmetric band matrix (S dense
+ * row-major n x n, half-bandwidth kd) with this handle's reduced-camera-block solver (LDL^T or QR by variant). */
+int ba_debug_band_solve(ba_handle* h, int n, int kd, const double* S, const double* g, double* y);
 int ba_timer_start(ba_handle* h);
 int ba_timer_stop(ba_handle* h, double* elapsed_ms);
 

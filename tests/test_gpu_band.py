@@ -1,0 +1,75 @@
+"""GPU (-m gpu): the reduced-camera-block solver in isolation (ba_debug_band_solve) against numpy on
+random symmetric positive-definite band systems: ragged sizes (n not a multiple of the 32-wide panel),
+half-bandwidths below / at / above one panel, dense (kd = n-1), both LDL^T paths (one-cluster kernel and
+the cooperative-grid kernel) and the Householder QR path. Replaces SimplicialLDLT::compute/solve and
+DenseBlockedThinQR (BacktrackLevMarqQRChol.h:339-341, BAFunctor.h:101,111)."""
+import os
+
+import numpy as np
+import pytest
+
+from bundleadjustment_benchmarks_b200 import bal, solver
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(18, 17), (33, 5), (64, 31), (100, 32), (189, 188), (351, 98), (700, 44), (1000, 548), (2313, 300)]
+
+
+def band_spd(n, kd, seed):
+    rng = np.random.default_rng(seed)
+    A = np.zeros((n, n))
+    for d in range(1, kd + 1):
+        v = rng.standard_normal(n - d)
+        A += np.diag(v, -d) + np.diag(v, d)
+    A += np.diag(np.abs(A).sum(axis=1) + rng.uniform(0.5, 2.0, n))
+    return A, rng.standard_normal(n)
+
+
+def _solve(variant, precision, force_grid):
+    prob = bal.synthetic(4, 40, seed=3)
+    if force_grid:
+        os.environ["BA_FORCE_GRID_LDLT"] = "1"
+    try:
+        s = solver.GpuSolver(prob, variant, precision)
+    finally:
+        os.environ.pop("BA_FORCE_GRID_LDLT", None)
+    return s
+
+
+@pytest.mark.parametrize("path", ["cluster", "grid", "qr"])
+def test_band_solve_matches_numpy(path):
+    s = _solve("QRKIT" if path == "qr" else "QRCHOL", "f64", path == "grid")
+    for i, (n, kd) in enumerate(CASES):
+        if path == "qr" and n > 1000:
+            continue
+        A, g = band_spd(n, kd, 100 + i)
+        y = s.debug_band_solve(A, g, kd)
+        ref = np.linalg.solve(A, g)
+        err = np.linalg.norm(y - ref) / np.linalg.norm(ref)
+        assert err < 1e-12, (path, n, kd, err)
+    s.close()
+
+
+def test_band_solve_indefinite_ldlt():
+    """SimplicialLDLT semantics: un-pivoted LDL^T also factors symmetric indefinite matrices (D < 0 allowed)."""
+    s = _solve("QRCHOL", "f64", False)
+    n, kd = 300, 40
+    A, g = band_spd(n, kd, 7)
+    sgn = np.where(np.arange(n) % 3 == 0, -1.0, 1.0)
+    A = A * sgn[:, None] * sgn[None, :]
+    A[::5, ::5] *= 1.0
+    A = A - 2.0 * np.diag(np.diag(A)) * (np.arange(n) % 7 == 0)
+    ref = np.linalg.solve(A, g)
+    y = s.debug_band_solve(A, g, kd)
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 1e-10
+    s.close()
+
+
+def test_band_solve_float():
+    s = _solve("QRCHOL", "f32", False)
+    for i, (n, kd) in enumerate(CASES[:7]):
+        A, g = band_spd(n, kd, 200 + i)
+        y = s.debug_band_solve(A, g, kd)
+        ref = np.linalg.solve(A, g)
+        assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 2e-5, (n, kd)
+    s.close()
