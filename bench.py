@@ -267,15 +267,21 @@ def run_ours(args):
         stage += s.stage_ms()
     stage /= nprof
     s.set_profiling(False)
-    names = ["init_S", "k_schur", "all_reduce", "factor", "reduced_solve", "k_cam_update", "k_backsub_eval", "reductions"]
+    names = ["k_point_factor", "k_schur_gather", "all_reduce", "factor", "reduced_solve", "k_cam_update", "k_backsub_eval", "reductions"]
     sz = 4 if args.precision == "f32" else 8
     N, M, K = prob.N, prob.M, prob.K
     bw = s.bandwidth
     kd = min(9 * N - 1, 9 * bw + 8)
     band_bytes = 9 * N * (kd + 1) * sz
+    pairs = int(sum(n * (n + 1) // 2 for n in np.bincount(prob.point, minlength=M)))
+    rec = 36 * sz  # bytes of one per-observation record (csrc/ba_tile.cuh)
     alg_bytes = {
-        "k_schur": K * (8 + 2 * sz) + 3 * M * sz + 16 * N * sz + 9 * N * sz + band_bytes,
-        "k_backsub_eval": K * (8 + 2 * sz) + 9 * M * sz + 2 * 16 * N * sz + 9 * N * sz,
+        # observations in (indices, measurement), points + cameras in, P and Q records + point records out
+        "k_point_factor": K * (12 + 2 * sz) + 3 * M * sz + 16 * N * sz + 2 * K * rec + 16 * M * sz,
+        # every P record once for the pair sums (re-reads are served by L2), every Q record once for the
+        # diagonal blocks, the pair list, S band + g + gJ out
+        "k_schur_gather": 2 * K * rec + 8 * pairs + band_bytes + 2 * 9 * N * sz,
+        "k_backsub_eval": K * (12 + 2 * sz) + K * rec + 16 * M * sz + 9 * M * sz + 2 * 16 * N * sz + 9 * N * sz,
         "factor": 2 * band_bytes,
         "reduced_solve": band_bytes + 3 * 9 * N * sz,
     }

@@ -144,16 +144,17 @@ __global__ void __launch_bounds__(256) k_max(const T* __restrict__ v, int n, dou
 
 // cams_test = update(cams, dx_cam) (update_params, BAFunctor.h:311-333) and |dx_cam|^2. One CTA.
 template <class T>
-__global__ void __launch_bounds__(1024) k_cam_update(int N, const T* __restrict__ cams, const T* __restrict__ dx_cam, T* __restrict__ cams_test,
-                                                     double* __restrict__ out_norm2) {
+__global__ void __launch_bounds__(1024) k_cam_update(int N, const T* __restrict__ cams, const T* __restrict__ dx_cam, const T* __restrict__ gJ,
+                                                     T* __restrict__ cams_test, double* __restrict__ out_norm2, double* __restrict__ out_dot) {
   __shared__ double s[1024];
-  double acc = 0.0;
+  __shared__ double s2[1024];
+  double acc = 0.0, acc2 = 0.0;
   for (int c = threadIdx.x; c < N; c += 1024) {
     const T* ci = cams + (size_t)c * CAM_STRIDE;
     T* co = cams_test + (size_t)c * CAM_STRIDE;
     T d[9];
 #pragma unroll
-    for (int b = 0; b < 9; ++b) { d[b] = dx_cam[9 * (size_t)c + b]; acc += (double)(d[b] * d[b]); }
+    for (int b = 0; b < 9; ++b) { d[b] = dx_cam[9 * (size_t)c + b]; acc += (double)(d[b] * d[b]); acc2 += (double)(d[b] * gJ[9 * (size_t)c + b]); }
     T Rin[9], Rout[9];
 #pragma unroll
     for (int b = 0; b < 9; ++b) Rin[b] = ci[b];
@@ -163,10 +164,10 @@ __global__ void __launch_bounds__(1024) k_cam_update(int N, const T* __restrict_
     co[9] = ci[9] + d[0]; co[10] = ci[10] + d[1]; co[11] = ci[11] + d[2];
     co[12] = ci[12] + d[6]; co[13] = ci[13] + d[7]; co[14] = ci[14] + d[8]; co[15] = T(0);
   }
-  s[threadIdx.x] = acc;
+  s[threadIdx.x] = acc; s2[threadIdx.x] = acc2;
   __syncthreads();
-  for (int off = 512; off > 0; off >>= 1) { if ((int)threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off]; __syncthreads(); }
-  if (threadIdx.x == 0) out_norm2[0] = s[0];
+  for (int off = 512; off > 0; off >>= 1) { if ((int)threadIdx.x < off) { s[threadIdx.x] += s[threadIdx.x + off]; s2[threadIdx.x] += s2[threadIdx.x + off]; } __syncthreads(); }
+  if (threadIdx.x == 0) { out_norm2[0] = s[0]; out_dot[0] = s2[0]; }
 }
 
 template <class T> __global__ void k_neg_copy(const T* __restrict__ a, T* __restrict__ b, int n, T sign) {
@@ -230,6 +231,10 @@ struct Impl : ba_handle {
   cudaEvent_t ev[9];
   cudaEvent_t tev[2] = {nullptr, nullptr};
   DevBuf<int> d_view, d_point, d_pt_start, d_tile_pt, d_info;
+  DevBuf<int> d_slot, d_cam_start, d_blk_a, d_blk_b, d_blk_start, d_blk_order, d_counter;  // static structure of the deterministic Schur gather
+  DevBuf<int2> d_pairs;
+  DevBuf<T> d_P, d_Q, d_Pt;  // per-observation / per-point records written by k_point_factor
+  int nblocks = 0, gather_grid = 0;
   DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g */, d_keep, d_y, d_dvec, d_tmp;
   DevBuf<T> d_qr;  // general band copy for the Householder QR of S
   DevBuf<T> d_W;   // L_kk^-1 tiles kept by the cluster LDLT for the backward pass
@@ -258,6 +263,7 @@ struct Impl : ba_handle {
   size_t lds() const { return (size_t)ldsv; }
   static int pad_lds(int kd_) { const int a = 16 / (int)sizeof(T); return (kd_ + a - 1) / a * a; }
   T* gvec() { return d_red.p + red_count; }
+  T* gJvec() { return d_red.p + red_count + n; }  // sum_i Jc_i^T e_i per camera (rho denominator)
   BandMat<T> band() { return BandMat<T>{Sv(), lds(), n, kd}; }
   static constexpr ncclDataType_t nccl_t() { return sizeof(T) == 8 ? ncclDouble : ncclFloat; }
 
@@ -267,7 +273,7 @@ struct Impl : ba_handle {
     n = 9 * N;
     ldsv = pad_lds(kd);
     red_count = (size_t)n * (ldsv + 1);
-    CK(d_red.alloc(red_count + n));
+    CK(d_red.alloc(red_count + 2 * (size_t)n));
     CK(d_y.alloc(n)); CK(d_dvec.alloc(n));
     if (keep_reduced) CK(d_keep.alloc(red_count + n));
     d_qr.free();
@@ -304,6 +310,45 @@ struct Impl : ba_handle {
     tile_pt.push_back(M);
     ntiles = (int)tile_pt.size() - 1;
 
+    // static structure of the Schur gather: camera-major record slots, non-empty camera-pair blocks, pair lists
+    std::vector<int> cam_start(N + 1, 0), slot(K);
+    for (int i = 0; i < K; ++i) cam_start[view[i] + 1]++;
+    for (int c = 0; c < N; ++c) cam_start[c + 1] += cam_start[c];
+    {
+      std::vector<int> fill(cam_start.begin(), cam_start.end() - 1);
+      for (int i = 0; i < K; ++i) slot[i] = fill[view[i]]++;
+    }
+    const size_t Wd = (size_t)bw + 1;
+    if ((size_t)N * Wd > (size_t)1 << 30) return fail(BA_ERR_ARG, "camera-pair table too large (N = %d, bandwidth = %d)", N, bw);
+    std::vector<int> cnt((size_t)N * Wd, 0);
+    for (int j = 0; j < M; ++j)
+      for (int ia = pt_start[j]; ia < pt_start[j + 1]; ++ia)
+        for (int ib = pt_start[j]; ib < ia; ++ib) cnt[(size_t)view[ia] * Wd + (view[ia] - view[ib])]++;
+    std::vector<int> blk_a, blk_b, blk_start, pos((size_t)N * Wd, -1);
+    long long npairs_ll = 0;
+    for (int a2 = 0; a2 < N; ++a2)
+      for (int dl = 1; dl <= bw && dl <= a2; ++dl) {  // diagonal blocks are streamed by k_schur_diag
+        const size_t key = (size_t)a2 * Wd + dl;
+        if (cnt[key] > 0) {
+          blk_a.push_back(a2); blk_b.push_back(a2 - dl); blk_start.push_back((int)npairs_ll);
+          pos[key] = (int)npairs_ll; npairs_ll += cnt[key];
+          if (npairs_ll > 2000000000LL) return fail(BA_ERR_ARG, "too many camera-pair contributions for 32-bit offsets");
+        }
+      }
+    blk_start.push_back((int)npairs_ll);
+    nblocks = (int)blk_a.size();
+    std::vector<int2> pairs((size_t)std::max<long long>(npairs_ll, 1));
+    for (int j = 0; j < M; ++j)
+      for (int ia = pt_start[j]; ia < pt_start[j + 1]; ++ia)
+        for (int ib = pt_start[j]; ib < ia; ++ib) {
+          const size_t key = (size_t)view[ia] * Wd + (view[ia] - view[ib]);
+          pairs[pos[key]++] = make_int2(slot[ia], slot[ib]);
+        }
+    { std::vector<int>().swap(cnt); std::vector<int>().swap(pos); }
+    std::vector<int> blk_order(nblocks);  // largest first: longest-processing-time order for the dynamic scheduler
+    for (int b2 = 0; b2 < nblocks; ++b2) blk_order[b2] = b2;
+    std::stable_sort(blk_order.begin(), blk_order.end(), [&](int x, int y) { return blk_start[x + 1] - blk_start[x] > blk_start[y + 1] - blk_start[y]; });
+
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BA_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
     CK(cudaSetDevice(device));
@@ -321,6 +366,17 @@ struct Impl : ba_handle {
     CK(cudaMemcpyAsync(d_point.p, point, K * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_pt_start.p, pt_start.data(), (M + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_tile_pt.p, tile_pt.data(), (ntiles + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(d_slot.alloc(K)); CK(d_cam_start.alloc(N + 1)); CK(d_blk_a.alloc(nblocks)); CK(d_blk_b.alloc(nblocks)); CK(d_blk_start.alloc(nblocks + 1));
+    CK(d_blk_order.alloc(nblocks)); CK(d_counter.alloc(1));
+    CK(cudaMemcpyAsync(d_blk_order.p, blk_order.data(), nblocks * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(d_pairs.alloc(pairs.size()));
+    CK(d_P.alloc((size_t)K * REC)); CK(d_Q.alloc((size_t)K * REC)); CK(d_Pt.alloc((size_t)M * PREC));
+    CK(cudaMemcpyAsync(d_slot.p, slot.data(), K * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_cam_start.p, cam_start.data(), (N + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_blk_a.p, blk_a.data(), nblocks * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_blk_b.p, blk_b.data(), nblocks * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_blk_start.p, blk_start.data(), (nblocks + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_pairs.p, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
     std::vector<T> m(2 * (size_t)K);
     for (size_t i = 0; i < m.size(); ++i) m[i] = (T)meas[i];
     CK(cudaMemcpyAsync(d_meas.p, m.data(), m.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
@@ -329,10 +385,11 @@ struct Impl : ba_handle {
     CK(cudaStreamSynchronize(stream));
     int rc = alloc_reduced();
     if (rc) return rc;
-    CK(cudaFuncSetAttribute(k_schur<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<T>)));
-    CK(cudaFuncSetAttribute(k_backsub_eval<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<T>)));
+    CK(cudaFuncSetAttribute(k_point_factor<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<T>)));
     int occ = 0, sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_schur_gather<T>, GATHER_THREADS, 0));
+    gather_grid = std::max(1, std::min(std::max(occ, 1) * sms, (nblocks + GATHER_THREADS / 32 - 1) / (GATHER_THREADS / 32)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_ldlt<T>, DENSE_THREADS, 0));
     coop_grid = std::max(1, std::min(occ, 2)) * sms;
     if (const char* cs = std::getenv("BA_CLUSTER_SIZE")) cluster_size = std::max(1, std::min(16, atoi(cs)));
@@ -459,14 +516,20 @@ struct Impl : ba_handle {
     const T sl = (T)std::sqrt(lamT);
     const T diag = (variant == BA_CHOLESKY) ? lamT : sl * sl;  // QR variants square the sqrt(lambda) rows
     mark(0);
-    CK(cudaMemsetAsync(d_red.p, 0, (red_count + n) * sizeof(T), stream));
-    if (rank == 0) { k_add_diag<T><<<(n + 255) / 256, 256, 0, stream>>>(Sv(), lds(), n, diag); launches++; }
-    mark(1);
-    k_schur<T><<<ntiles, TILE, sizeof(TileSmem<T>), stream>>>(tile_args(lamT), Sv(), lds(), gvec());
+    CK(cudaMemsetAsync(d_red.p, 0, (red_count + 2 * (size_t)n) * sizeof(T), stream));
+    k_point_factor<T><<<ntiles, TILE, sizeof(TileSmem<T>), stream>>>(tile_args(lamT), d_slot.p, d_P.p, d_Q.p, d_Pt.p);
     launches++;
     CK(cudaGetLastError());
+    mark(1);
+    CK(cudaMemsetAsync(d_counter.p, 0, sizeof(int), stream));
+    k_schur_diag<T><<<N, GATHER_THREADS, 0, stream>>>(d_cam_start.p, d_P.p, d_Q.p, Sv(), lds(), gvec(), gJvec(), rank == 0 ? diag : T(0));
+    if (nblocks > 0)
+      k_schur_gather<T><<<gather_grid, GATHER_THREADS, 0, stream>>>(nblocks, d_blk_order.p, d_blk_a.p, d_blk_b.p, d_blk_start.p, d_pairs.p, d_P.p,
+                                                                     Sv(), lds(), d_counter.p);
+    launches += 2;
+    CK(cudaGetLastError());
     mark(2);
-    if (comm) NK(g_nccl.AllReduce(d_red.p, d_red.p, red_count + n, nccl_t(), ncclSum, comm, stream));
+    if (comm) NK(g_nccl.AllReduce(d_red.p, d_red.p, red_count + 2 * (size_t)n, nccl_t(), ncclSum, comm, stream));
     if (keep_reduced) {
       if (d_keep.n < red_count + n) CK(d_keep.alloc(red_count + n));
       CK(cudaMemcpyAsync(d_keep.p, d_red.p, (red_count + n) * sizeof(T), cudaMemcpyDeviceToDevice, stream));
@@ -558,11 +621,11 @@ struct Impl : ba_handle {
     { int rc = solve_reduced(); if (rc) return rc; }
     CK(cudaGetLastError());
     mark(5);
-    k_cam_update<T><<<1, 1024, 0, stream>>>(N, d_cams.p, d_dx_cam.p, d_cams_test.p, d_scal.p + 4);
+    k_cam_update<T><<<1, 1024, 0, stream>>>(N, d_cams.p, d_dx_cam.p, gJvec(), d_cams_test.p, d_scal.p + 4, d_scal.p + 6);
     launches++;
     mark(6);
-    k_backsub_eval<T><<<ntiles, TILE, sizeof(TileSmem<T>), stream>>>(tile_args(lamT), d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
-                                                                      d_partials.p, ntiles);
+    k_backsub_eval<T><<<ntiles, TILE, 0, stream>>>(tile_args(lamT), d_slot.p, d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
+                                                    d_partials.p, ntiles);
     launches++;
     CK(cudaGetLastError());
     mark(7);
@@ -570,7 +633,7 @@ struct Impl : ba_handle {
     launches++;
     int rc = allreduce_scal(1, 3);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h_scal, d_scal.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h_scal, d_scal.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(h_scal + 8, d_info.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
     mark(8);
     CK(cudaStreamSynchronize(stream));
@@ -578,7 +641,7 @@ struct Impl : ba_handle {
     collect(4, 8, stages);
     const double dx2 = h_scal[2] + h_scal[4];
     if (dx_norm) *dx_norm = std::sqrt(dx2);
-    if (rho_den) *rho_den = lambda * dx2 - h_scal[3];
+    if (rho_den) *rho_den = lambda * dx2 - h_scal[3] - h_scal[6];  // dx^T(lambda dx + JtRes), JtRes = -J^T r
     if (energy_test) *energy_test = h_scal[1];
     tried = true;
     return BA_OK;
@@ -686,8 +749,8 @@ struct Impl : ba_handle {
     const int n0 = n, kd0 = kd, lds0 = ldsv; const size_t rc0 = red_count;
     n = n_; kd = std::max(1, std::min(kd_, n_ - 1)); ldsv = pad_lds(kd); red_count = (size_t)n * (ldsv + 1);
     DevBuf<T> red, yv, dv, dxc;
-    CK(red.alloc(red_count + n)); CK(yv.alloc(n)); CK(dv.alloc(n)); CK(dxc.alloc(n));
-    std::vector<T> hb(red_count + n, T(0));
+    CK(red.alloc(red_count + 2 * (size_t)n)); CK(yv.alloc(n)); CK(dv.alloc(n)); CK(dxc.alloc(n));
+    std::vector<T> hb(red_count + 2 * (size_t)n, T(0));
     for (int i = 0; i < n; ++i)
       for (int j = std::max(0, i - kd); j <= i; ++j) hb[(size_t)ldsv + (size_t)i * ldsv + j] = (T)S[(size_t)i * n + j];
     for (int i = 0; i < n; ++i) hb[red_count + i] = (T)g[i];

@@ -1,5 +1,6 @@
-// Point-tile kernels for sm_100a: the fused Jacobian + per-point block factorisation + Schur
-// accumulation kernel (K2) and the fused back-substitution + update + test-energy kernel (K45).
+// Point-tile kernels for sm_100a: the fused Jacobian + per-point block factorisation kernel
+// (k_point_factor), the deterministic Schur gather (k_schur_gather) and the fused back-substitution +
+// update + test-energy kernel (k_backsub_eval).
 //
 // Replaces, on the device and without ever materialising J:
 //   row permutation + [J; sqrt(lambda) I]                  BacktrackLevMarqQRChol.h:291-315
@@ -273,12 +274,46 @@ __device__ __forceinline__ void tile_phases_123(const TileArgs<T>& a, TileSmem<T
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// K2: accumulate the reduced camera system. Sv/lds: band view of S (entry (i,j), j<=i, at
-// Sv[i*lds + j]); g[9N].  S_ab += delta_ab Jc_a^T Jc_a - R12_a^T R12_b ; g_a += Jc_a^T e_a - R12_a^T c.
-// ---------------------------------------------------------------------------------------------
+// =============================================================================================
+// Deterministic two-pass Schur accumulation (no atomics).
+//
+// FP64 global reductions issue at ~1.3 cycles per lane per SM (tools/ubench; 1.34e9 of them = 6 ms at the
+// synthetic scale) and make S differ from run to run. The structure of S is static (which point
+// contributes to which 9x9 camera-pair block), so it is built once on the host: every non-empty block
+// (a, b), b <= a, owns the list of (observation of a, observation of b) pairs of the points seen by both.
+// Pass 1 (k_point_factor, one CTA per point tile) stores per observation, at the observation's
+// CAMERA-MAJOR slot (observations sorted by (camera, point)),
+//   P record (36 scalars): R12_i = Q1_i^T Jc_i as [k][g][4] = {R12[k][3g..3g+2], 0}
+//   Q record (36 scalars): Jc_i as [r][g][4] = {Jc[r][3g..3g+2], e_r}, then [g][4] = {gobs[3g..3g+2], 0},
+//                          gobs = Jc^T e - R12^T c
+// and per point (R (6), c (3), G = Jp^T e (3), perm, pad) = 16 scalars.
+// Pass 2 (k_schur_gather, one warp per block) sums -R12_a^T R12_b over the block's pair list with 3x3
+// register tiles (9 lanes per pair, three pairs in flight per warp, fixed order), adds Jc^T Jc, g and
+// gJ = sum Jc^T e on the diagonal blocks and WRITES the block: every entry of S has exactly one writer,
+// so the result is bit-reproducible. Camera-major slots keep the working set of consecutive blocks (the
+// records of ~bw cameras) in L2. The back-substitution re-reads the P and point records instead of
+// re-evaluating the Jacobian and the point QR.
+// =============================================================================================
+constexpr int REC = 36;   // scalars per observation record
+constexpr int PREC = 16;  // scalars per point record
+
+__device__ __forceinline__ void store4(double* p, double a, double b, double c, double d) {
+  *reinterpret_cast<double2*>(p) = make_double2(a, b);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
+}
+__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+__device__ __forceinline__ void load4(const double* p, double& a, double& b, double& c, double& d) {
+  const double2 u = __ldg(reinterpret_cast<const double2*>(p)), v = __ldg(reinterpret_cast<const double2*>(p + 2));
+  a = u.x; b = u.y; c = v.x; d = v.y;
+}
+__device__ __forceinline__ void load4(const float* p, float& a, float& b, float& c, float& d) {
+  const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+  a = u.x; b = u.y; c = u.z; d = u.w;
+}
+
 template <class T>
-__global__ void __launch_bounds__(TILE) k_schur(TileArgs<T> a, T* __restrict__ Sv, size_t lds, T* __restrict__ g) {
+__global__ void __launch_bounds__(TILE) k_point_factor(TileArgs<T> a, const int* __restrict__ slot, T* __restrict__ Prec, T* __restrict__ Qrec,
+                                                       T* __restrict__ Ptrec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<T>& sm = *reinterpret_cast<TileSmem<T>*>(smem_raw);
   const int t = threadIdx.x, tile = blockIdx.x;
@@ -286,105 +321,274 @@ __global__ void __launch_bounds__(TILE) k_schur(TileArgs<T> a, T* __restrict__ S
   const int o0 = a.pt_start[p0], nobs = a.pt_start[p1] - o0;
   int cam_idx, lp;
   tile_phases_123<T>(a, sm, t, p0, npts, o0, nobs, cam_idx, lp);
-  // pair offsets
-  if (t < npts) { const int n = sm.ptN[t]; sm.pairOff[t + 1] = n * (n + 1) / 2; }
-  if (t == 0) sm.pairOff[0] = 0;
   __syncthreads();
-  if (t == 0) { int s = 0; for (int p = 0; p < npts; ++p) { s += sm.pairOff[p + 1]; sm.pairOff[p + 1] = s; } }
-  // g contributions (one lane per observation)
   if (t < nobs) {
+    const size_t sl = (size_t)__ldg(slot + o0 + t);
+    T* pr = Prec + sl * REC;
+    T* qr = Qrec + sl * REC;
     const T e0 = sm.E[t], e1 = sm.E[TP + t];
     const T c0 = sm.C[lp], c1 = sm.C[TP + lp], c2 = sm.C[2 * TP + lp];
 #pragma unroll
-    for (int b = 0; b < 9; ++b) {
-      const T v = sm.Jc[b * TP + t] * e0 + sm.Jc[(9 + b) * TP + t] * e1
-                - (sm.R12[b * TP + t] * c0 + sm.R12[(9 + b) * TP + t] * c1 + sm.R12[(18 + b) * TP + t] * c2);
-      atomic_add<T>(g + 9 * (size_t)cam_idx + b, v);
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+        store4(pr + 12 * k + 4 * g, sm.R12[(9 * k + 3 * g) * TP + t], sm.R12[(9 * k + 3 * g + 1) * TP + t], sm.R12[(9 * k + 3 * g + 2) * TP + t], T(0));
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+        store4(qr + 12 * r + 4 * g, sm.Jc[(9 * r + 3 * g) * TP + t], sm.Jc[(9 * r + 3 * g + 1) * TP + t], sm.Jc[(9 * r + 3 * g + 2) * TP + t], r == 0 ? e0 : e1);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      T v[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int b = 3 * g + i;
+        v[i] = sm.Jc[b * TP + t] * e0 + sm.Jc[(9 + b) * TP + t] * e1
+             - (sm.R12[b * TP + t] * c0 + sm.R12[(9 + b) * TP + t] * c1 + sm.R12[(18 + b) * TP + t] * c2);
+      }
+      store4(qr + 24 + 4 * g, v[0], v[1], v[2], T(0));
+    }
+  }
+  if (t < npts) {
+    T* q = Ptrec + (size_t)(p0 + t) * PREC;
+    store4(q, sm.Rm[0 * TP + t], sm.Rm[1 * TP + t], sm.Rm[2 * TP + t], sm.Rm[3 * TP + t]);
+    store4(q + 4, sm.Rm[4 * TP + t], sm.Rm[5 * TP + t], sm.C[t], sm.C[TP + t]);
+    store4(q + 8, sm.C[2 * TP + t], sm.G[t], sm.G[TP + t], sm.G[2 * TP + t]);
+    store4(q + 12, (T)sm.perm[t], T(0), T(0), T(0));
+  }
+}
+
+// Off-diagonal blocks: one warp per block (a, b), b < a, blocks handed out largest-first through a global
+// counter (the result does not depend on which warp computes a block). Lanes 0..26: group = lane / 9 takes
+// every third pair, (P, Q) = 3x3 tile of the 9x9 block; lanes 27..31 idle. Two pairs per group are in
+// flight and the pair indices are fetched one batch ahead, so one memory latency is exposed per two pairs.
+constexpr int GATHER_THREADS = 256;
+template <class T>
+__global__ void __launch_bounds__(GATHER_THREADS, 2) k_schur_gather(int nblocks, const int* __restrict__ blk_order, const int* __restrict__ blk_a,
+                                                                    const int* __restrict__ blk_b, const int* __restrict__ blk_start,
+                                                                    const int2* __restrict__ pairs, const T* __restrict__ Prec,
+                                                                    T* __restrict__ Sv, size_t lds, int* __restrict__ counter) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / 9, li = lane - 9 * grp, P = li / 3, Q = li - 3 * P;
+  const bool act = grp < 3;
+  while (true) {
+    int bi = 0;
+    if (lane == 0) bi = atomicAdd(counter, 1);
+    bi = __shfl_sync(FULL, bi, 0);
+    if (bi >= nblocks) break;
+    const int B = __ldg(blk_order + bi);
+    const int ca = __ldg(blk_a + B), cb = __ldg(blk_b + B);
+    const int s0 = __ldg(blk_start + B), s1 = __ldg(blk_start + B + 1);
+    T acc[3][3] = {{T(0), T(0), T(0)}, {T(0), T(0), T(0)}, {T(0), T(0), T(0)}};
+    if (act) {
+      int t = s0 + grp;
+      int2 n0 = make_int2(0, 0), n1 = make_int2(0, 0);
+      if (t < s1) n0 = __ldg(pairs + t);
+      if (t + 3 < s1) n1 = __ldg(pairs + t + 3);
+      while (t < s1) {
+        const int2 c0 = n0, c1 = n1;
+        const bool two = t + 3 < s1;
+        t += 6;
+        if (t < s1) n0 = __ldg(pairs + t);
+        if (t + 3 < s1) n1 = __ldg(pairs + t + 3);
+        const T* pa0 = Prec + (size_t)c0.x * REC + 4 * P;
+        const T* pb0 = Prec + (size_t)c0.y * REC + 4 * Q;
+        const T* pa1 = Prec + (size_t)(two ? c1.x : c0.x) * REC + 4 * P;
+        const T* pb1 = Prec + (size_t)(two ? c1.y : c0.y) * REC + 4 * Q;
+        T a0[3][4], b0[3][4], a1[3][4], b1[3][4];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          load4(pa0 + 12 * k, a0[k][0], a0[k][1], a0[k][2], a0[k][3]); load4(pb0 + 12 * k, b0[k][0], b0[k][1], b0[k][2], b0[k][3]);
+          load4(pa1 + 12 * k, a1[k][0], a1[k][1], a1[k][2], a1[k][3]); load4(pb1 + 12 * k, b1[k][0], b1[k][1], b1[k][2], b1[k][3]);
+        }
+        const T m1 = two ? T(1) : T(0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const T x1 = a1[k][i] * m1;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { acc[i][j] -= a0[k][i] * b0[k][j]; acc[i][j] -= x1 * b1[k][j]; }
+          }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const T v1 = __shfl_down_sync(FULL, acc[i][j], 9), v2 = __shfl_down_sync(FULL, acc[i][j], 18);
+        acc[i][j] = (acc[i][j] + v1) + v2;
+      }
+    if (lane < 9) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Sv[(size_t)(9 * ca + 3 * P + i) * lds + 9 * cb + 3 * Q + j] = acc[i][j];
+    }
+  }
+}
+
+// Diagonal blocks: one CTA per camera streams the camera's (contiguous, camera-major) records:
+// S_aa = sum_i Jc_i^T Jc_i - R12_i^T R12_i (+ lambda I), g_a = sum_i gobs_i, gJ_a = sum_i Jc_i^T e_i.
+// 24 lane groups (8 warps x 3) stride over the records, two records per group in flight; per-warp shuffle
+// reduction, then a fixed-order sum over the 8 warps in shared memory (bit-reproducible).
+template <class T>
+__global__ void __launch_bounds__(GATHER_THREADS, 2) k_schur_diag(const int* __restrict__ cam_start, const T* __restrict__ Prec, const T* __restrict__ Qrec,
+                                                                  T* __restrict__ Sv, size_t lds, T* __restrict__ g, T* __restrict__ gJ, T lambda_diag) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int NW = GATHER_THREADS / 32;
+  __shared__ T part[NW][9][15];  // per warp, per 3x3 tile lane: 9 block entries + 3 g + 3 gJ
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ca = blockIdx.x;
+  const int grp = lane / 9, li = lane - 9 * grp, P = li / 3, Q = li - 3 * P;
+  const bool act = grp < 3;
+  const int q0 = __ldg(cam_start + ca), q1 = __ldg(cam_start + ca + 1);
+  T acc[3][3] = {{T(0), T(0), T(0)}, {T(0), T(0), T(0)}, {T(0), T(0), T(0)}};
+  T gacc[3] = {T(0), T(0), T(0)}, jacc[3] = {T(0), T(0), T(0)};
+  if (act) {
+    for (int sidx = q0 + warp * 3 + grp; sidx < q1; sidx += 2 * 3 * NW) {
+      const bool two = sidx + 3 * NW < q1;
+      const size_t r0 = (size_t)sidx * REC, r1 = (size_t)(two ? sidx + 3 * NW : sidx) * REC;
+      T ap[2][3][4], aq[2][3][4], jp[2][2][4], jq[2][2][4], gv[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const size_t r = u ? r1 : r0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          load4(Prec + r + 12 * k + 4 * P, ap[u][k][0], ap[u][k][1], ap[u][k][2], ap[u][k][3]);
+          load4(Prec + r + 12 * k + 4 * Q, aq[u][k][0], aq[u][k][1], aq[u][k][2], aq[u][k][3]);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          load4(Qrec + r + 12 * rr + 4 * P, jp[u][rr][0], jp[u][rr][1], jp[u][rr][2], jp[u][rr][3]);
+          load4(Qrec + r + 12 * rr + 4 * Q, jq[u][rr][0], jq[u][rr][1], jq[u][rr][2], jq[u][rr][3]);
+        }
+        load4(Qrec + r + 24 + 4 * P, gv[u][0], gv[u][1], gv[u][2], gv[u][3]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const T m = (u == 0 || two) ? T(1) : T(0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            T v = jp[u][0][i] * jq[u][0][j] + jp[u][1][i] * jq[u][1][j];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) v -= ap[u][k][i] * aq[u][k][j];
+            acc[i][j] += m * v;
+          }
+          gacc[i] += m * gv[u][i];
+          jacc[i] += m * (jp[u][0][i] * jp[u][0][3] + jp[u][1][i] * jp[u][1][3]);
+        }
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const T v1 = __shfl_down_sync(FULL, acc[i][j], 9), v2 = __shfl_down_sync(FULL, acc[i][j], 18);
+      acc[i][j] = (acc[i][j] + v1) + v2;
+    }
+    const T u1 = __shfl_down_sync(FULL, gacc[i], 9), u2 = __shfl_down_sync(FULL, gacc[i], 18);
+    gacc[i] = (gacc[i] + u1) + u2;
+    const T w1 = __shfl_down_sync(FULL, jacc[i], 9), w2 = __shfl_down_sync(FULL, jacc[i], 18);
+    jacc[i] = (jacc[i] + w1) + w2;
+  }
+  if (lane < 9) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) part[warp][lane][3 * i + j] = acc[i][j];
+      part[warp][lane][9 + i] = gacc[i];
+      part[warp][lane][12 + i] = jacc[i];
     }
   }
   __syncthreads();
-  // phase 4: one warp per (point, ia >= ib) pair; lanes <-> entries of the 9x9 block
-  const int lane = t & 31, warp = t >> 5, nwarps = TILE / 32;
-  const int npairs = sm.pairOff[npts];
-  int ep[3], eq[3];
+  if (warp == 0 && lane < 9) {
+    T tot[15];
 #pragma unroll
-  for (int s = 0; s < 3; ++s) { const int e = lane + 32 * s; ep[s] = e / 9; eq[s] = e - 9 * ep[s]; }
-  for (int q = warp; q < npairs; q += nwarps) {
-    int lo_ = 0, hi_ = npts;  // largest p with pairOff[p] <= q
-    while (hi_ - lo_ > 1) { const int mid = (lo_ + hi_) >> 1; if (sm.pairOff[mid] <= q) lo_ = mid; else hi_ = mid; }
-    const int pp = lo_, ql = q - sm.pairOff[pp];
-    int ia = (int)((sqrtf(8.0f * (float)ql + 1.0f) - 1.0f) * 0.5f);
-    while ((ia + 1) * (ia + 2) / 2 <= ql) ++ia;
-    while (ia * (ia + 1) / 2 > ql) --ia;
-    const int ib = ql - ia * (ia + 1) / 2;
-    const int oa = sm.ptObs0[pp] + ia, ob = sm.ptObs0[pp] + ib;
-    const int ca = __ldg(a.view + o0 + oa), cb = __ldg(a.view + o0 + ob);  // ca >= cb (sorted by camera)
+    for (int e = 0; e < 15; ++e) { T v = T(0); for (int w = 0; w < NW; ++w) v += part[w][lane][e]; tot[e] = v; }
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int e = lane + 32 * s;
-      if (e >= 81) continue;
-      const int p = ep[s], qq = eq[s];
-      if (ia == ib && qq > p) continue;
-      T v = -(sm.R12[p * TP + oa] * sm.R12[qq * TP + ob] + sm.R12[(9 + p) * TP + oa] * sm.R12[(9 + qq) * TP + ob] +
-              sm.R12[(18 + p) * TP + oa] * sm.R12[(18 + qq) * TP + ob]);
-      if (ia == ib) v += sm.Jc[p * TP + oa] * sm.Jc[qq * TP + oa] + sm.Jc[(9 + p) * TP + oa] * sm.Jc[(9 + qq) * TP + oa];
-      atomic_add<T>(Sv + (size_t)(9 * ca + p) * lds + (9 * cb + qq), v);
+    for (int i = 0; i < 3; ++i) {
+      const int row = 9 * ca + 3 * P + i;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int col = 9 * ca + 3 * Q + j;
+        if (col < row) Sv[(size_t)row * lds + col] = tot[3 * i + j];
+        else if (col == row) Sv[(size_t)row * lds + col] = tot[3 * i + j] + lambda_diag;
+      }
+      if (Q == 0) { g[row] = tot[9 + i]; gJ[row] = tot[12 + i]; }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K45: back-substitution, state update and test-point energy, fused.
+// Back-substitution, state update and test-point energy, fused, from the stored records:
 //   dx_j = R_j^-1 (-c_j - sum_i R12_i dx_cam(i)) un-permuted; X_test = X + dx_j;
 //   e_test = residual(cams_test, X_test); partial sums per tile:
-//     part[0] = sum e_test^2, part[1] = |dx_pts|^2, part[2] = sum_obs e.(J dx)  (so that
-//     dx^T(lambda dx + JtRes) = lambda |dx|^2 - part[2]).
+//     part[0] = sum e_test^2, part[1] = |dx_pts|^2, part[2] = sum_points G . dx_j (G = Jp^T e), so that
+//     dx^T(lambda dx + JtRes) = lambda |dx|^2 - part[2] - dx_cam . gJ.
 // ---------------------------------------------------------------------------------------------
 template <class T>
-__global__ void __launch_bounds__(TILE) k_backsub_eval(TileArgs<T> a, const T* __restrict__ dx_cam, const T* __restrict__ cams_test,
+__global__ void __launch_bounds__(TILE) k_backsub_eval(TileArgs<T> a, const int* __restrict__ slot, const T* __restrict__ Prec,
+                                                       const T* __restrict__ Ptrec, const T* __restrict__ dx_cam, const T* __restrict__ cams_test,
                                                        T* __restrict__ dx_pt, T* __restrict__ X_test, double* __restrict__ partials, int ntiles) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<T>& sm = *reinterpret_cast<TileSmem<T>*>(smem_raw);
+  __shared__ T su[3][TP];
+  __shared__ T sx[3][TP];
+  __shared__ double red[3 * (TILE / 32)];
   const int t = threadIdx.x, tile = blockIdx.x;
   const int p0 = a.tile_pt[tile], p1 = a.tile_pt[tile + 1], npts = p1 - p0;
   const int o0 = a.pt_start[p0], nobs = a.pt_start[p1] - o0;
-  int cam_idx, lp;
-  tile_phases_123<T>(a, sm, t, p0, npts, o0, nobs, cam_idx, lp);
   double acc_e = 0.0, acc_dx = 0.0, acc_jd = 0.0;
-  // per observation: u_i = R12_i dx_cam(i) (3) -> E rows reused after reading e; e.(Jc dx_cam)
-  T u0 = T(0), u1 = T(0), u2 = T(0);
+  int cam_idx = 0, lp = 0;
   if (t < nobs) {
+    const int i = o0 + t;
+    cam_idx = __ldg(a.view + i);
+    lp = __ldg(a.point + i) - p0;
+    const T* pr = Prec + (size_t)__ldg(slot + i) * REC;
     T d[9];
 #pragma unroll
     for (int b = 0; b < 9; ++b) d[b] = __ldg(dx_cam + 9 * (size_t)cam_idx + b);
-    T j0 = T(0), j1 = T(0);
 #pragma unroll
-    for (int b = 0; b < 9; ++b) {
-      u0 += sm.R12[b * TP + t] * d[b]; u1 += sm.R12[(9 + b) * TP + t] * d[b]; u2 += sm.R12[(18 + b) * TP + t] * d[b];
-      j0 += sm.Jc[b * TP + t] * d[b]; j1 += sm.Jc[(9 + b) * TP + t] * d[b];
+    for (int k = 0; k < 3; ++k) {
+      T u = T(0);
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        T r0, r1, r2, r3;
+        load4(pr + 12 * k + 4 * g, r0, r1, r2, r3);
+        u += r0 * d[3 * g] + r1 * d[3 * g + 1] + r2 * d[3 * g + 2];
+      }
+      su[k][t] = u;
     }
-    acc_jd += (double)(sm.E[t] * j0 + sm.E[TP + t] * j1);
   }
-  __syncthreads();  // all reads of Jc done; reuse Jc rows 0..2 as per-observation u
-  if (t < nobs) { sm.Jc[0 * TP + t] = u0; sm.Jc[1 * TP + t] = u1; sm.Jc[2 * TP + t] = u2; }
   __syncthreads();
   if (t < npts) {
-    const int lo = sm.ptObs0[t], n = sm.ptN[t];
-    T r0 = -sm.C[t], r1 = -sm.C[TP + t], r2 = -sm.C[2 * TP + t];
-    for (int i = 0; i < n; ++i) { r0 -= sm.Jc[0 * TP + lo + i]; r1 -= sm.Jc[1 * TP + lo + i]; r2 -= sm.Jc[2 * TP + lo + i]; }
-    const T z2 = r2 / sm.Rm[5 * TP + t];
-    const T z1 = (r1 - sm.Rm[4 * TP + t] * z2) / sm.Rm[3 * TP + t];
-    const T z0 = (r0 - sm.Rm[1 * TP + t] * z1 - sm.Rm[2 * TP + t] * z2) / sm.Rm[0 * TP + t];
-    const int pm = sm.perm[t];
+    const int lo = a.pt_start[p0 + t] - o0, n = a.pt_start[p0 + t + 1] - a.pt_start[p0 + t];
+    const T* q = Ptrec + (size_t)(p0 + t) * PREC;
+    T R00, R01, R02, R11, R12v, R22, c0, c1, c2, G0, G1, G2, pf, z_, z1_, z2_;
+    load4(q, R00, R01, R02, R11);
+    load4(q + 4, R12v, R22, c0, c1);
+    load4(q + 8, c2, G0, G1, G2);
+    load4(q + 12, pf, z_, z1_, z2_);
+    T r0 = -c0, r1 = -c1, r2 = -c2;
+    for (int i = 0; i < n; ++i) { r0 -= su[0][lo + i]; r1 -= su[1][lo + i]; r2 -= su[2][lo + i]; }
+    const T z2 = r2 / R22;
+    const T z1 = (r1 - R12v * z2) / R11;
+    const T z0 = (r0 - R01 * z1 - R02 * z2) / R00;
+    const int pm = (int)pf;
     T d[3];
     d[pm & 3] = z0; d[(pm >> 2) & 3] = z1; d[(pm >> 4) & 3] = z2;
     const size_t gp = 3 * (size_t)(p0 + t);
     acc_dx += (double)(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    acc_jd += (double)(sm.G[t] * d[0] + sm.G[TP + t] * d[1] + sm.G[2 * TP + t] * d[2]);
+    acc_jd += (double)(G0 * d[0] + G1 * d[1] + G2 * d[2]);
     dx_pt[gp] = d[0]; dx_pt[gp + 1] = d[1]; dx_pt[gp + 2] = d[2];
     const T x0 = __ldg(a.X + gp) + d[0], x1 = __ldg(a.X + gp + 1) + d[1], x2 = __ldg(a.X + gp + 2) + d[2];
     X_test[gp] = x0; X_test[gp + 1] = x1; X_test[gp + 2] = x2;
-    sm.G[t] = x0; sm.G[TP + t] = x1; sm.G[2 * TP + t] = x2;
+    sx[0][t] = x0; sx[1][t] = x1; sx[2][t] = x2;
   }
   __syncthreads();
   if (t < nobs) {
@@ -392,10 +596,9 @@ __global__ void __launch_bounds__(TILE) k_backsub_eval(TileArgs<T> a, const T* _
     const int i = o0 + t;
     const T m0 = __ldg(a.meas + 2 * (size_t)i), m1 = __ldg(a.meas + 2 * (size_t)i + 1);
     T e0, e1;
-    obs_residual<T>(c, sm.G[lp], sm.G[TP + lp], sm.G[2 * TP + lp], m0, m1, a.tau2, e0, e1);
+    obs_residual<T>(c, sx[0][lp], sx[1][lp], sx[2][lp], m0, m1, a.tau2, e0, e1);
     acc_e += (double)(e0 * e0 + e1 * e1);
   }
-  // block reduction (deterministic order)
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     acc_e += __shfl_down_sync(0xffffffffu, acc_e, off);
@@ -403,11 +606,11 @@ __global__ void __launch_bounds__(TILE) k_backsub_eval(TileArgs<T> a, const T* _
     acc_jd += __shfl_down_sync(0xffffffffu, acc_jd, off);
   }
   const int lane = t & 31, warp = t >> 5;
-  if (lane == 0) { sm.red[warp] = acc_e; sm.red[TILE / 32 + warp] = acc_dx; sm.red[2 * (TILE / 32) + warp] = acc_jd; }
+  if (lane == 0) { red[warp] = acc_e; red[TILE / 32 + warp] = acc_dx; red[2 * (TILE / 32) + warp] = acc_jd; }
   __syncthreads();
   if (t < 3) {
     double s = 0.0;
-    for (int w = 0; w < TILE / 32; ++w) s += sm.red[t * (TILE / 32) + w];
+    for (int w = 0; w < TILE / 32; ++w) s += red[t * (TILE / 32) + w];
     partials[(size_t)t * ntiles + tile] = s;
   }
 }
