@@ -242,19 +242,29 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = max_over_ranks(dev_ms) / args.steps
 
-    # ---- end-to-end region: host buffers through the C ABI every step
-    R, T, f, k1, k2, X = [np.ascontiguousarray(a) for a in (prob.R, prob.T, prob.f, prob.k1, prob.k2, prob.X)]
+    # ---- end-to-end region: PINNED host buffers through the C ABI every step (state upload + step download)
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
+        return t, t.numpy()
+    keep, (R, T, f, k1, k2, X) = zip(*[pinned(a) for a in (prob.R, prob.T, prob.f, prob.k1, prob.k2, prob.X)])
+    dx_t = torch.empty(3 * prob.M + 9 * prob.N, dtype=torch.float64).pin_memory()
+    dx_h = dx_t.numpy()
     h2d = sum(a.nbytes for a in (R, T, f, k1, k2, X))
-    d2h = 8 * (3 * prob.M + 9 * prob.N) + 6 * 8
+    d2h = dx_h.nbytes + 3 * 8
     e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        s.set_state(R, T, f, k1, k2, X)
+        out = step()
+        s.dx_into(dx_h)
+        return out
+
     for _ in range(2):
-        s.set_state(R, T, f, k1, k2, X); step(); s.dx()
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        s.set_state(R, T, f, k1, k2, X)
-        step()
-        s.dx()
+        e2e_step()
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
 
@@ -292,7 +302,6 @@ def run_ours(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = alg_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
@@ -300,14 +309,31 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get(f"{args.workload}:{args.variant}:{args.precision}", {}).get(dom)
         except Exception:
             traffic = None
-    kernel_name = {"factor": "k_band_ldlt" if args.variant in ("QRCHOL", "CHOLESKY") else "k_band_qr",
-                   "reduced_solve": "k_band_ldlt_solve" if args.variant in ("QRCHOL", "CHOLESKY") else "k_band_qr_backsolve"}.get(dom, dom)
-    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes": alg_bytes[dom], "kernel_ms": dom_ms,
-                "stages_ms": {n: float(v) for n, v in zip(names, stage)},
-                "hbm_frac_by_kernel": {k: (alg_bytes[k] / (stage[names.index(k)] * 1e-3) / 1e9 / peak) if stage[names.index(k)] > 0 else None
-                                       for k in alg_bytes}}
+    kernel_name = {"factor": "k_band_ldlt_cluster" if args.variant in ("QRCHOL", "CHOLESKY") else "k_band_qr",
+                   "reduced_solve": "k_band_ldlt_cluster (solve folded in)" if args.variant in ("QRCHOL", "CHOLESKY") else "k_band_qr_backsolve",
+                   "k_schur_gather": "k_schur_diag + k_schur_gather"}.get(dom, dom)
+    n_red = 9 * N
+    if dom == "factor":
+        # the band factorisation is an FP64 contraction (n kd^2 flops for LDL^T, 4x for Householder QR of the
+        # square band) on the FP64 tensor pipe (DMMA); peak = 64 FMA/clk/SM measured with tools/ubench
+        # (DMMA m8n8k4 and DFMA both) x 148 SMs x max SM clock
+        flops = float(n_red) * kd * kd * (1.0 if args.variant in ("QRCHOL", "CHOLESKY") else 4.0)
+        fp64_peak = 64 * 2 * 148 * 1.965e9 / 1e12
+        achieved = flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": kernel_name, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp64_peak, "traffic": traffic,
+                    "peak_source": "FP64 DMMA/DFMA issue rate measured with tools/ubench (64 FMA/clk/SM) x 148 SMs x 1.965 GHz; "
+                                   "the kernel runs on ONE 16-CTA cluster (latency-bound panel chain), see DESIGN.md",
+                    "algorithmic_flops": flops, "kernel_ms": dom_ms}
+    else:
+        achieved = alg_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes": alg_bytes[dom], "kernel_ms": dom_ms}
+    roofline["stages_ms"] = {n: float(v) for n, v in zip(names, stage)}
+    roofline["hbm_frac_by_kernel"] = {k: (alg_bytes[k] / (stage[names.index(k)] * 1e-3) / 1e9 / peak) if stage[names.index(k)] > 0 else None
+                                      for k in ("k_point_factor", "k_schur_gather", "k_backsub_eval")}
+    roofline["hbm_peak"] = {"value": peak, "unit": "GB/s", "source": peak_src}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:

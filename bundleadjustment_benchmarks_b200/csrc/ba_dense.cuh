@@ -738,21 +738,21 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
       const bool active = ci <= last && cj <= ci && (ci - cj) * NB - (NB - 1) <= kd;
       const bool interior = active && (ci != cj) && (ci * NB + NB - 1 < n) && (ci * NB + NB - 1 - cj * NB <= kd);
       T* cp = Av + (size_t)(ci * NB) * lds + cj * NB;
-      T acc[32];
+      T cc[32];  // C fragments: loaded here, added after the DMMAs (their latency hides behind the tile product)
       if (interior) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
           for (int ni = 0; ni < 4; ++ni) {
             const V2 v = *reinterpret_cast<const V2*>(cp + (mi * 8 + lr) * lds + ni * 8 + 2 * lc);
-            acc[2 * (4 * mi + ni)] = v.x; acc[2 * (4 * mi + ni) + 1] = v.y;
+            cc[2 * (4 * mi + ni)] = v.x; cc[2 * (4 * mi + ni) + 1] = v.y;
           }
       } else if (active) {
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const int r = (e >> 3) * 8 + lr, c = ((e >> 1) & 3) * 8 + 2 * lc + (e & 1), gi = ci * NB + r, gj = cj * NB + c;
           const bool ok = gi < n && gj <= gi && gi - gj <= kd;
-          acc[e] = *(ok ? cp + r * lds + c : zp);
+          cc[e] = *(ok ? cp + r * lds + c : zp);
         }
       }
       cp_async_wait_all();
@@ -760,7 +760,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
       p = rank + C * sm.grab[team][slot];
       if (p < count) { decode(p, bi, bj); stage_block(buf ^ 1, bi, bj); }
       if (active) {
+        T acc[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = T(0);
         block_mma(sm.gA[team][buf][tw >> 1], sm.gB[team][buf][tw & 1], sd, lane, acc);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] += cc[e];
         if (interior) {
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi)

@@ -87,6 +87,7 @@ class GpuSolver:
 
     # --- state
     def set_state(self, R, T, f, k1, k2, X):
+        # no copy when the caller hands in contiguous float64 (e.g. pinned) buffers
         arrs = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (R, T, f, k1, k2, X)]
         self._ck(self._L.ba_set_state(self._h, *[_dp(a) for a in arrs]))
 
@@ -129,6 +130,12 @@ class GpuSolver:
         v = np.empty(self.n)
         self._ck(self._L.ba_get_dx(self._h, _dp(v)))
         return v
+
+    def dx_into(self, out):
+        """Step download into a caller-owned (ideally pinned) float64 buffer of 3M+9N entries."""
+        assert out.dtype == np.float64 and out.size == self.n and out.flags["C_CONTIGUOUS"]
+        self._ck(self._L.ba_get_dx(self._h, _dp(out)))
+        return out
 
     def residuals(self):
         r = np.empty(2 * self.K)
