@@ -554,27 +554,117 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
 #pragma unroll
   for (int e = 0; e < 8; e += 2) { int r, c; frag_rc<T>(gt, e, r, c); coff[e >> 1] = r * lds + c; }
 
-  // ---- one panel of the chain: diagonal tile + row tiles of panel k (chain team only; team barriers)
+  // ---- tile (t, k) -> shared memory
+  auto stage_operand = [&](T (&dst)[NB][TS], const int t, const int k0) {
+    const int row0 = t * NB;
+    const bool interior = (row0 + NB - 1 < n) && (row0 + NB - 1 - k0 <= kd);
+    const T* tp = Av + (size_t)row0 * lds + k0;
+    if (interior) {
+#pragma unroll
+      for (int q = 0; q < NCP; ++q) cp_async16(&dst[0][0] + soff[q], tp + aoff[q]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int idx = gt + 128 * q, r = idx >> 5, c = idx & 31, gi = row0 + r;
+        const bool ok = gi < n && gi - (k0 + c) <= kd;
+        dst[r][c] = *(ok ? tp + r * lds + c : zp);
+      }
+    }
+  };
+  // ---- one panel of the chain (chain team only; team barriers): the column-k tiles first receive panel
+  // k-1's update (the diagonal tile by the four warps together, every CTA redundantly; each row tile by the
+  // warp that will solve it, one warp = one 32x32 DMMA tile product, while warp 0 factors), then
+  // diagonal factor, row-tile substitutions, W_k, publication. No cluster-level phase for column k.
+  auto stage_tile_warp = [&](T (&dst)[NB][TS], const int t, const int c0) {  // tile (t, c0/NB) by ONE warp
+    const int row0 = t * NB;
+    const bool interior = (row0 + NB - 1 < n) && (row0 + NB - 1 - c0 <= kd);
+    const T* tp = Av + (size_t)row0 * lds + c0;
+    if (interior) {
+#pragma unroll
+      for (int q = 0; q < NB * CPR / 32; ++q) { const int id = lane + 32 * q, r = id / CPR, ch = id % CPR; cp_async16(&dst[r][ch * EPC], tp + r * lds + ch * EPC); }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        const int gi = row0 + lane;
+        const bool ok = gi < n && gi - (c0 + c) <= kd;
+        dst[lane][c] = *(ok ? tp + lane * lds + c : zp);
+      }
+    }
+  };
   auto chain = [&](const int k) {
     const int k0 = k * NB, last = min(nt - 1, k + bt);
-    for (int idx = gt; idx < NB * NB; idx += 128) {
-      const int r = idx >> 5, c = idx & 31, gi = k0 + r, gj = k0 + c;
-      const bool ok = gi < n && c <= r && gi - gj <= kd;
-      const T v = *(ok ? Av + (size_t)gi * lds + gj : zp);
-      sm.sL[r][c] = (gi >= n && r == c) ? T(1) : v;
-    }
-    if (gt < NB) sm.pn.sz[gt] = *((k0 + gt < n) ? rhs + k0 + gt : zp);
-    // row-tile warps prefetch their rows (lane = row) while the diagonal tile is factored. Work items of
-    // warps 1..3: the CTA's row tiles it = k+1+rank+C*u; warp 3 of CTA k%C first forms W_k (identity rows).
+    const bool upd = k > 0;
+    const int kp0 = (k - 1) * NB;
+    const T* sdp = sm.sdU[(k - 1) & 1];
+    T (&sBop)[NB][TS] = sm.gB[0][0][0];            // L(k, k-1): column operand of every column-k update
+    T (&wbuf)[NB][TS] = sm.gA[0][tw >> 1][tw & 1];  // per-warp tile buffer
+    const int lr = lane >> 2, lc = lane & 3;
+    if (upd) stage_operand(sBop, k, kp0);
+    // row-tile warps: work items of warps 1..3 are the CTA's row tiles it = k+1+rank+C*u; warp 3 of CTA k%C first
+    // forms W_k (identity rows). The first tile is fetched (and updated) while the diagonal tile is factored.
     T a[NB];
     const bool w_warp = (tw == 3) && (rank == k % C);
     int it = k + 1 + rank + C * (tw - 1);
     bool pre = (tw >= 1) && !w_warp && (it <= last);
-    if (pre) {
-      const int gi = it * NB + lane;
-      const T* rp = Av + (size_t)gi * lds + k0;
+    auto fetch_issue = [&](const int t, bool& use_mma) {  // start fetching row tile (t, k): operand + C fragments, or plain rows
+      use_mma = upd && (t <= k - 1 + bt);
+      if (use_mma) {
+        stage_tile_warp(wbuf, t, kp0);
+      } else {
+        const int gi = t * NB + lane;
+        const T* rp = Av + (size_t)gi * lds + k0;
 #pragma unroll
-      for (int c = 0; c < NB; ++c) { const bool ok = gi < n && gi - (k0 + c) <= kd; a[c] = *(ok ? rp + c : zp); }
+        for (int c = 0; c < NB; ++c) { const bool ok = gi < n && gi - (k0 + c) <= kd; a[c] = *(ok ? rp + c : zp); }
+      }
+    };
+    auto fetch_finish = [&](const int t) {  // operands landed (caller synchronised): tile product, then rows into registers
+      T acc[32], prod[32];
+      const T* cp = Av + (size_t)(t * NB) * lds + k0;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int r = (e >> 3) * 8 + lr, c = ((e >> 1) & 3) * 8 + 2 * lc + (e & 1), gi = t * NB + r;
+        const bool ok = gi < n && gi - (k0 + c) <= kd;
+        acc[e] = *(ok ? cp + r * lds + c : zp);
+        prod[e] = T(0);
+      }
+      block_mma(wbuf, sBop, sdp, lane, prod);
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int r = (e >> 3) * 8 + lr, c = ((e >> 1) & 3) * 8 + 2 * lc + (e & 1);
+        wbuf[r][c] = acc[e] + prod[e];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < NB; ++c) a[c] = wbuf[lane][c];
+      __syncwarp();
+    };
+    bool pre_mma = false;
+    if (pre) fetch_issue(it, pre_mma);
+    cp_async_commit();
+    // diagonal tile C fragments (quadrant layout of tile_mma)
+    T cc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int r, c; frag_rc<T>(gt, e, r, c);
+      const int gi = k0 + r, gj = k0 + c;
+      const bool ok = gi < n && c <= r && gi - gj <= kd;
+      cc[e] = *(ok ? Av + (size_t)gi * lds + gj : zp);
+    }
+    const T zr = *((gt < NB && k0 + gt < n) ? rhs + k0 + gt : zp);
+    cp_async_wait_all();
+    group_barrier(0);
+    {
+      T dacc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dacc[e] = T(0);
+      if (upd) tile_mma(sBop, sBop, sdp, gt, dacc);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int r, c; frag_rc<T>(gt, e, r, c);
+        sm.sL[r][c] = (k0 + r >= n && r == c) ? T(1) : cc[e] + dacc[e];
+      }
+      if (gt < NB) sm.pn.sz[gt] = zr;
     }
     group_barrier(0);
     if (tw == 0) {
@@ -586,6 +676,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
       const T d = sm.pn.sd[lane];
       sm.sdU[k & 1][lane] = d;
       if (rank == 0 && k0 + lane < n && (d == T(0) || !(d == d))) atomicCAS(info, 0, k0 + lane + 1);
+    } else if (pre && pre_mma) {
+      fetch_finish(it);
     }
     group_barrier(0);
     if (tw >= 1) {
@@ -596,9 +688,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
 #pragma unroll
           for (int c = 0; c < NB; ++c) a[c] = (c == lane) ? T(1) : T(0);
         } else if (!pre) {
-          const T* rp = Av + (size_t)gi * lds + k0;
-#pragma unroll
-          for (int c = 0; c < NB; ++c) { const bool ok = gi < n && gi - (k0 + c) <= kd; a[c] = *(ok ? rp + c : zp); }
+          bool um = false;
+          fetch_issue(it, um);
+          cp_async_commit();
+          cp_async_wait_all();
+          __syncwarp();
+          if (um) fetch_finish(it);
         }
         pre = false;
         // one substitution call site (code size): W mode = identity rows, x[c] = W(c, lane), un-scaled;
@@ -621,83 +716,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
       }
       if (gt < NB && k0 + gt < n) { dvec[k0 + gt] = sm.pn.sd[gt]; rhs[k0 + gt] = sm.pn.sz[gt] * sm.pn.sinvd[gt]; }
     }
-    group_barrier(0);  // everyone is done with pn before the next chain() overwrites it
-  };
-
-  // ---- tile (t, k) -> shared memory
-  auto stage_operand = [&](T (&dst)[NB][TS], const int t, const int k0) {
-    const int row0 = t * NB;
-    const bool interior = (row0 + NB - 1 < n) && (row0 + NB - 1 - k0 <= kd);
-    const T* tp = Av + (size_t)row0 * lds + k0;
-    if (interior) {
-#pragma unroll
-      for (int q = 0; q < NCP; ++q) cp_async16(&dst[0][0] + soff[q], tp + aoff[q]);
-    } else {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int idx = gt + 128 * q, r = idx >> 5, c = idx & 31, gi = row0 + r;
-        const bool ok = gi < n && gi - (k0 + c) <= kd;
-        dst[r][c] = *(ok ? tp + r * lds + c : zp);
-      }
-    }
-  };
-  // ---- a phase of tile updates with panel k: items p = rank + C*t handed out through sm.work.
-  // col_phase: tiles (k+1+p, k+1); otherwise tiles (i, j), k+2 <= j <= i <= last, p = ii(ii+1)/2 + jj.
-  auto tile_phase = [&](const int k, const bool col_phase) {
-    const int k0 = k * NB, last = min(nt - 1, k + bt), nb = last - k;
-    const int count = col_phase ? nb : (nb - 1) * nb / 2;
-    const T* sd = sm.sdU[k & 1];
-    auto decode = [&](int p, int& ti, int& tj) {
-      if (col_phase) { ti = k + 1 + p; tj = k + 1; return; }
-      int ii = (int)((__fsqrt_rn(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-      while ((ii + 1) * (ii + 2) / 2 <= p) ++ii;
-      while (ii * (ii + 1) / 2 > p) --ii;
-      ti = k + 2 + ii; tj = k + 2 + (p - ii * (ii + 1) / 2);
-    };
-    int slot = 0, buf = 0, ti = 0, tj = 0;
-    if (gt == 0) sm.grab[team][0] = atomicAdd(&sm.work, 1);
-    group_barrier(team);
-    int p = rank + C * sm.grab[team][0];
-    if (p < count) { decode(p, ti, tj); stage_operand(sm.gA[team][0][0], ti, k0); stage_operand(sm.gB[team][0][0], tj, k0); cp_async_commit(); }
-    while (p < count) {
-      const int ci = ti, cj = tj;
-      slot ^= 1;
-      if (gt == 0) sm.grab[team][slot] = atomicAdd(&sm.work, 1);
-      cp_async_wait_all();
-      group_barrier(team);  // operands landed; next item visible; everyone is done with the other buffer
-      p = rank + C * sm.grab[team][slot];
-      if (p < count) { decode(p, ti, tj); stage_operand(sm.gA[team][buf ^ 1][0], ti, k0); stage_operand(sm.gB[team][buf ^ 1][0], tj, k0); cp_async_commit(); }
-      T* cp = Av + (size_t)(ci * NB) * lds + cj * NB;
-      const bool interior = (ci != cj) && (ci * NB + NB - 1 < n) && (ci * NB + NB - 1 - cj * NB <= kd);
-      T cc[8], acc[8];
-      if (sizeof(T) == 8 && interior) {
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) { const V2 v = *reinterpret_cast<const V2*>(cp + coff[e >> 1]); cc[e] = v.x; cc[e + 1] = v.y; }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          int r, c; frag_rc<T>(gt, e, r, c);
-          const int gi = ci * NB + r, gj = cj * NB + c;
-          const bool ok = gi < n && gj <= gi && gi - gj <= kd;
-          cc[e] = *(ok ? cp + r * lds + c : zp);
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = T(0);
-      tile_mma(sm.gA[team][buf][0], sm.gB[team][buf][0], sd, gt, acc);
-      if (sizeof(T) == 8 && interior) {
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) { V2 v; v.x = cc[e] + acc[e]; v.y = cc[e + 1] + acc[e + 1]; *reinterpret_cast<V2*>(cp + coff[e >> 1]) = v; }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          int r, c; frag_rc<T>(gt, e, r, c);
-          const int gi = ci * NB + r, gj = cj * NB + c;
-          if (gi < n && gj <= gi && gi - gj <= kd) cp[r * lds + c] = cc[e] + acc[e];
-        }
-      }
-      buf ^= 1;
-    }
+    group_barrier(0);  // everyone is done with pn and the team's tile buffers before they are reused
   };
 
   // ---- the remaining tiles (columns >= k+2) receive panel k's update in 2x2 blocks of tiles: block (I, J),
@@ -786,20 +805,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
     }
   };
 
-  // ================= factorisation with one panel of look-ahead
+  // ================= factorisation with one panel of look-ahead: per panel ONE cluster barrier.
+  // Iteration k: chain(k+1) (which first gives column k+1 panel k's update) runs next to the update of
+  // the columns >= k+2 with panel k; the chain team joins the update when it is done.
   __syncthreads();
   if (team == 0) chain(0);
   cluster.sync();
   for (int k = 0; k < nt; ++k) {
-    tile_phase(k, true);                       // phase B(k): column k+1 <- panel k
-    __syncthreads();
-    if (tid == 0) sm.work = 0;
-    TICK(0)
-    cluster.sync();
     TICK(1)
-    if (team == 0 && k + 1 < nt) chain(k + 1); // phase A(k+1): next panel's chain ...
+    if (team == 0 && k + 1 < nt) chain(k + 1);
     TICK(2)
-    block_phase(k);                            // ... while columns >= k+2 <- panel k (2x2 tile blocks)
+    block_phase(k);
     TICK(3)
     __syncthreads();
     if (tid == 0) sm.work = 0;

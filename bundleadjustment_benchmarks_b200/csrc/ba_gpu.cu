@@ -238,7 +238,7 @@ struct Impl : ba_handle {
   DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g */, d_keep, d_y, d_dvec, d_tmp;
   DevBuf<T> d_qr;  // general band copy for the Householder QR of S
   DevBuf<T> d_W;   // L_kk^-1 tiles kept by the cluster LDLT for the backward pass
-  int cluster_size = 8;
+  int cluster_size = 16;  // non-portable size; falls back to 8 when 16 CTAs of this footprint cannot be co-scheduled
   bool solved_in_factor = false;
   DevBuf<double> d_partials, d_scal;
   DevBuf<long long> d_dbg;
@@ -396,9 +396,20 @@ struct Impl : ba_handle {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_ldlt<T>, DENSE_THREADS, 0));
     coop_grid = std::max(1, std::min(occ, 2)) * sms;
     if (const char* cs = std::getenv("BA_CLUSTER_SIZE")) cluster_size = std::max(1, std::min(16, atoi(cs)));
-    if (cluster_size > 8) CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     if (std::getenv("BA_FORCE_GRID_LDLT")) force_grid_ldlt = true;
     CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterSmem<T>)));
+    CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    for (; cluster_size > 1; cluster_size /= 2) {  // largest cluster the device can co-schedule
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cluster_size); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = sizeof(ClusterSmem<T>);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, k_band_ldlt_cluster<T>, &cfg) == cudaSuccess && nclusters >= 1) break;
+      cudaGetLastError();
+    }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_qr<T>, QR_THREADS, 0));
     coop_grid_qr = std::max(1, std::min(occ, 2)) * sms;
     return BA_OK;
