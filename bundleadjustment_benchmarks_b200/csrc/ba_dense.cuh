@@ -271,7 +271,7 @@ template <class T> struct ClusterSmem {
   alignas(16) T sLk[2][NB][NB + 1];
   alignas(16) T sWk[2][NB][NB + 1];
   alignas(16) T sw[2][NB];
-  int work;                       // dynamic tile-op counter of the current phase
+  int work[2];                    // cluster-wide block-op counters (CTA 0's copy is used), alternating by panel parity
   int grab[CL_GROUPS][2];
   long long tc[16];
 };
@@ -540,11 +540,25 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
   long long t0 = clock64();
   if (tid < 16) sm.tc[tid] = 0;
   if (tid < 2 * NB) { sm.pn.sCol[0][NB + (tid & 31)] = T(0); sm.pn.sCol[1][NB + (tid & 31)] = T(0); }
-  if (tid == 0) sm.work = 0;
+  if (tid == 0) { sm.work[0] = 0; sm.work[1] = 0; }
+  // chain CTAs (ranks < NC) run the panel chain with all 8 warps (warp 0 factors, warps 1..7 own the row tiles);
+  // the other CTAs only update, so that the chain never shares an FP64 pipe with bulk DMMA work (measured:
+  // the register factorisation took 6.4 us instead of 2.7 us per panel next to an update team, profiles/)
+  // row tiles live on the six warps that do not share an SMSP with the factoring warp 0 (warps 1-3, 5-7);
+  // warp 4 (same SMSP as warp 0) only forms W_k, after the factorisation
+  constexpr int ROWW = CL_WARPS - 2;
+  const int NC = min(max(1, C / 4), (bt + ROWW - 1) / ROWW);
+  int* const work0 = cluster.map_shared_rank(&sm.work[0], 0);
 #ifdef BA_DENSE_TICKS
 #define TICK(i) { if (threadIdx.x == 128) { const long long t1_ = clock64(); sm.tc[i] += t1_ - t0; t0 = t1_; } __syncwarp(); }
 #else
 #define TICK(i) {}
+#endif
+#ifdef BA_DENSE_TICKS
+  long long t2 = clock64();
+#define TICKC(i) { if (threadIdx.x == 32) { const long long t1_ = clock64(); sm.tc[i] += t1_ - t2; t2 = t1_; } __syncwarp(); }
+#else
+#define TICKC(i) {}
 #endif
   // per-thread constants of the tile-op path
   int aoff[NCP], soff[NCP];
@@ -597,15 +611,19 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
     const int kp0 = (k - 1) * NB;
     const T* sdp = sm.sdU[(k - 1) & 1];
     T (&sBop)[NB][TS] = sm.gB[0][0][0];            // L(k, k-1): column operand of every column-k update
-    T (&wbuf)[NB][TS] = sm.gA[0][tw >> 1][tw & 1];  // per-warp tile buffer
+    T (&wbuf)[NB][TS] = *(reinterpret_cast<T (*)[NB][TS]>(&sm.gA[0][0][0][0][0]) + warp);  // per-warp tile buffer (8 of the 8+8 slots)
     const int lr = lane >> 2, lc = lane & 3;
-    if (upd) stage_operand(sBop, k, kp0);
-    // row-tile warps: work items of warps 1..3 are the CTA's row tiles it = k+1+rank+C*u; warp 3 of CTA k%C first
-    // forms W_k (identity rows). The first tile is fetched (and updated) while the diagonal tile is factored.
+    TICKC(13)
+    if (upd && tid < 128) stage_operand(sBop, k, kp0);
+    // row-tile warps: work items of warps 1..7 of the NC chain CTAs are the row tiles it = k+1+u, u = rank + NC*(warp-1)
+    // (+ NC*7 per further pass); the last warp of chain CTA k%NC first forms W_k (identity rows). The first tile is
+    // fetched (and updated) while the diagonal tile is factored.
     T a[NB];
-    const bool w_warp = (tw == 3) && (rank == k % C);
-    int it = k + 1 + rank + C * (tw - 1);
-    bool pre = (tw >= 1) && !w_warp && (it <= last);
+    const bool w_warp = (warp == 4) && (rank == k % NC);
+    const bool row_warp = (warp & 3) != 0;
+    const int ri = (warp < 4) ? warp - 1 : warp - 2;  // 0..5 over warps 1,2,3,5,6,7
+    int it = row_warp ? k + 1 + rank + NC * ri : last + 1;
+    bool pre = row_warp && (it <= last);
     auto fetch_issue = [&](const int t, bool& use_mma) {  // start fetching row tile (t, k): operand + C fragments, or plain rows
       use_mma = upd && (t <= k - 1 + bt);
       if (use_mma) {
@@ -651,10 +669,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
       const bool ok = gi < n && c <= r && gi - gj <= kd;
       cc[e] = *(ok ? Av + (size_t)gi * lds + gj : zp);
     }
-    const T zr = *((gt < NB && k0 + gt < n) ? rhs + k0 + gt : zp);
+    const T zr = *((tid < NB && k0 + tid < n) ? rhs + k0 + tid : zp);
     cp_async_wait_all();
-    group_barrier(0);
-    {
+    __syncthreads();
+    TICKC(8)
+    if (tid < 128) {
       T dacc[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) dacc[e] = T(0);
@@ -664,10 +683,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
         int r, c; frag_rc<T>(gt, e, r, c);
         sm.sL[r][c] = (k0 + r >= n && r == c) ? T(1) : cc[e] + dacc[e];
       }
-      if (gt < NB) sm.pn.sz[gt] = zr;
+      if (tid < NB) sm.pn.sz[tid] = zr;
     }
-    group_barrier(0);
-    if (tw == 0) {
+    __syncthreads();
+    TICKC(9)
+    if (warp == 0) {
       const T z = sm.pn.sz[lane];
 #pragma unroll
       for (int c = 0; c < NB; ++c) a[c] = (c <= lane) ? sm.sL[lane][c] : T(0);
@@ -679,44 +699,72 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
     } else if (pre && pre_mma) {
       fetch_finish(it);
     }
-    group_barrier(0);
-    if (tw >= 1) {
+    TICKC(10)
+    __syncthreads();
+    TICKC(11)
+    if (warp == 0 && rank == 0) {  // idle after the factorisation: publish the factored diagonal tile, D and w_k = D^-1 z_k
+#pragma unroll 4
+      for (int c = 0; c < NB; ++c) {
+        const int gi = k0 + lane, gj = k0 + c;  // lane = row: sLT[c][lane] is conflict-free
+        if (gi < n && gj <= gi && gi - gj <= kd) Av[(size_t)gi * lds + gj] = (c == lane) ? sm.pn.sd[c] : sm.pn.sLT[c][lane];
+      }
+      dvec[k0 + lane] = sm.pn.sd[lane];
+      if (k0 + lane < n) rhs[k0 + lane] = sm.pn.sz[lane] * sm.pn.sinvd[lane];
+    }
+    if (warp >= 1) {
       bool do_w = w_warp;
       while (do_w || it <= last) {
         const int gi = it * NB + lane;
+        T rold = T(0);
         if (do_w) {
 #pragma unroll
           for (int c = 0; c < NB; ++c) a[c] = (c == lane) ? T(1) : T(0);
-        } else if (!pre) {
-          bool um = false;
-          fetch_issue(it, um);
-          cp_async_commit();
-          cp_async_wait_all();
-          __syncwarp();
-          if (um) fetch_finish(it);
+        } else {
+          if (gi < n) rold = rhs[gi];
+          if (!pre) {
+            bool um = false;
+            fetch_issue(it, um);
+            cp_async_commit();
+            cp_async_wait_all();
+            __syncwarp();
+            if (um) fetch_finish(it);
+          }
         }
         pre = false;
-        // one substitution call site (code size): W mode = identity rows, x[c] = W(c, lane), un-scaled;
-        // tile mode = X L_kk^T = A_ik, L_ik = X D^-1, g_i -= L_ik z_k
-        T* out = do_w ? (Wbuf + (size_t)k * NB * NB + lane) : (Av + (size_t)gi * lds + k0);
+        // one substitution call site (code size). W mode: identity rows, x[c] = W(c, lane), un-scaled, straight to
+        // Wbuf. Tile mode: X L_kk^T = A_ik, L_ik = X D^-1 into the warp's tile buffer (row = lane), then written
+        // out with coalesced 16-byte stores; g_i -= L_ik z_k.
+        T* out = do_w ? (Wbuf + (size_t)k * NB * NB + lane) : &wbuf[lane][0];
         const int ostride = do_w ? NB : 1;
-        const int mmin = do_w ? 0 : ((gi < n) ? max(0, gi - k0 - kd) : NB);
-        const T s = warp_trsm32<T>(a, sm.pn, out, ostride, !do_w, mmin);
+        const T s = warp_trsm32<T>(a, sm.pn, out, ostride, !do_w, 0);
+        TICKC(12)
         if (do_w) do_w = false;
         else {
-          if (gi < n) rhs[gi] = rhs[gi] - s;
-          it += C * 3;
+          if (gi < n) rhs[gi] = rold - s;
+          __syncwarp();
+          T* tp = Av + (size_t)(it * NB) * lds + k0;
+          const bool interior = (it * NB + NB - 1 < n) && (it * NB + NB - 1 - k0 <= kd);
+          if (interior) {
+#pragma unroll
+            for (int q = 0; q < NB * CPR / 32; ++q) {
+              const int id = lane + 32 * q, r = id / CPR, ch = id % CPR;
+              *reinterpret_cast<V2*>(tp + r * lds + ch * EPC) = *reinterpret_cast<const V2*>(&wbuf[r][ch * EPC]);
+              if (EPC == 4) *reinterpret_cast<V2*>(tp + r * lds + ch * EPC + 2) = *reinterpret_cast<const V2*>(&wbuf[r][ch * EPC + 2]);
+            }
+          } else {
+            for (int c = 0; c < NB; ++c) {
+              const int g2 = it * NB + lane;
+              if (g2 < n && g2 - (k0 + c) <= kd) tp[lane * lds + c] = wbuf[lane][c];
+            }
+          }
+          __syncwarp();
+          it += NC * ROWW;
         }
       }
     }
-    if (rank == 0) {  // publish the factored diagonal tile, D and w_k = D^-1 z_k
-      for (int idx = gt; idx < NB * NB; idx += 128) {
-        const int r = idx >> 5, c = idx & 31, gi = k0 + r, gj = k0 + c;
-        if (gi < n && gj <= gi && gi - gj <= kd) Av[(size_t)gi * lds + gj] = (r == c) ? sm.pn.sd[c] : sm.pn.sLT[c][r];
-      }
-      if (gt < NB && k0 + gt < n) { dvec[k0 + gt] = sm.pn.sd[gt]; rhs[k0 + gt] = sm.pn.sz[gt] * sm.pn.sinvd[gt]; }
-    }
-    group_barrier(0);  // everyone is done with pn and the team's tile buffers before they are reused
+    TICKC(14)
+    __syncthreads();  // everyone is done with pn and the tile buffers before they are reused
+    TICKC(15)
   };
 
   // ---- the remaining tiles (columns >= k+2) receive panel k's update in 2x2 blocks of tiles: block (I, J),
@@ -744,15 +792,16 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
       cp_async_commit();
     };
     int slot = 0, buf = 0, bi = 0, bj = 0;
-    if (gt == 0) sm.grab[team][0] = atomicAdd(&sm.work, 1);
+    int* const wk = work0 + (k & 1);
+    if (gt == 0) sm.grab[team][0] = atomicAdd(wk, 1);
     group_barrier(team);
-    int p = rank + C * sm.grab[team][0];
+    int p = sm.grab[team][0];
     if (p < count) { decode(p, bi, bj); stage_block(0, bi, bj); }
     const int lr = lane >> 2, lc = lane & 3;
     while (p < count) {
       const int ci = k + 2 + 2 * bi + (tw >> 1), cj = k + 2 + 2 * bj + (tw & 1);  // this warp's tile
       slot ^= 1;
-      if (gt == 0) sm.grab[team][slot] = atomicAdd(&sm.work, 1);
+      if (gt == 0) sm.grab[team][slot] = atomicAdd(wk, 1);
       // C fragments straight into the accumulators (in flight while the operands land)
       const bool active = ci <= last && cj <= ci && (ci - cj) * NB - (NB - 1) <= kd;
       const bool interior = active && (ci != cj) && (ci * NB + NB - 1 < n) && (ci * NB + NB - 1 - cj * NB <= kd);
@@ -776,7 +825,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
       }
       cp_async_wait_all();
       group_barrier(team);  // operands landed; next item visible; everyone is done with the other buffer
-      p = rank + C * sm.grab[team][slot];
+      p = sm.grab[team][slot];
       if (p < count) { decode(p, bi, bj); stage_block(buf ^ 1, bi, bj); }
       if (active) {
         T acc[32];
@@ -809,16 +858,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
   // Iteration k: chain(k+1) (which first gives column k+1 panel k's update) runs next to the update of
   // the columns >= k+2 with panel k; the chain team joins the update when it is done.
   __syncthreads();
-  if (team == 0) chain(0);
+  if (rank < NC) chain(0);
   cluster.sync();
   for (int k = 0; k < nt; ++k) {
     TICK(1)
-    if (team == 0 && k + 1 < nt) chain(k + 1);
+    if (tid < NB) sm.sdU[k & 1][tid] = dvec[k * NB + tid];        // D_k (published by rank 0) for the updates
+    if (rank == 0 && tid == 0) sm.work[(k + 1) & 1] = 0;          // next panel's counter (idle during this one)
+    __syncthreads();
+    if (rank < NC && k + 1 < nt) chain(k + 1);
     TICK(2)
     block_phase(k);
     TICK(3)
-    __syncthreads();
-    if (tid == 0) sm.work = 0;
     cluster.sync();
     TICK(4)
   }
@@ -893,6 +943,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
   TICK(5)
   if (dbg && rank == 0 && tid == 128) for (int i = 0; i < 16; ++i) dbg[i] = sm.tc[i];
 #undef TICK
+#undef TICKC
 }
 
 }  // namespace ba

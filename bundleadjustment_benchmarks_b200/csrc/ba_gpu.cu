@@ -275,7 +275,7 @@ struct Impl : ba_handle {
     ldsv = pad_lds(kd);
     red_count = (size_t)n * (ldsv + 1);
     CK(d_red.alloc(red_count + 2 * (size_t)n));
-    CK(d_y.alloc(n)); CK(d_dvec.alloc(n));
+    CK(d_y.alloc(n)); CK(d_dvec.alloc((size_t)n + NB));  // D is read/written in whole 32-wide panels
     if (keep_reduced) CK(d_keep.alloc(red_count + n));
     d_qr.free();
     return BA_OK;
@@ -791,7 +791,7 @@ struct Impl : ba_handle {
     const int n0 = n, kd0 = kd, lds0 = ldsv; const size_t rc0 = red_count;
     n = n_; kd = std::max(1, std::min(kd_, n_ - 1)); ldsv = pad_lds(kd); red_count = (size_t)n * (ldsv + 1);
     DevBuf<T> red, yv, dv, dxc;
-    CK(red.alloc(red_count + 2 * (size_t)n)); CK(yv.alloc(n)); CK(dv.alloc(n)); CK(dxc.alloc(n));
+    CK(red.alloc(red_count + 2 * (size_t)n)); CK(yv.alloc(n)); CK(dv.alloc((size_t)n + NB)); CK(dxc.alloc(n));
     std::vector<T> hb(red_count + 2 * (size_t)n, T(0));
     for (int i = 0; i < n; ++i)
       for (int j = std::max(0, i - kd); j <= i; ++j) hb[(size_t)ldsv + (size_t)i * ldsv + j] = (T)S[(size_t)i * n + j];

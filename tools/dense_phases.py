@@ -7,7 +7,8 @@ for _ in range(3):
     s.compute(1e-12 * cn2); s.solve_try(); s.reject()
 s.set_profiling(True); s.compute(1e-12 * cn2); s.solve_try(); s.reject(); print("stage_ms", s.stage_ms())
 c = s.debug_counters()
-names = ["phaseB(col)", "sync", "chain(team0 only; t128 idle)", "phaseA(rest)", "sync", "backward(total)", "blk:loop top", "blk:grab+C load issue", "blk:wait+barrier", "blk:decode+stage next", "blk:mma", "blk:store"]
+names = ["-", "t128: loop top", "t128: (chain skipped)", "t128: block phase", "t128: syncthreads+cluster.sync", "backward(total)", "-", "-",
+         "w1: stage+wait+barrier", "w1: diag tile-op+barrier (idle)", "w1: fetch_finish (row tile update)", "w1: wait for factor", "w1: trsm", "w1: outside chain", "w1: write-out + rhs", "w1: end barrier"]
 nt = (9 * p.N + 31) // 32
 for n, v in zip(names, c):
-    print(f"{n:16s} {v:12d} cycles  = {v/1.9e3:9.1f} us total, {v/1.9e3/nt:6.2f} us/panel")
+    print(f"{n:42s} {v:12d} cycles  = {v/1.9e3:9.1f} us total, {v/1.9e3/nt:6.2f} us/panel")
