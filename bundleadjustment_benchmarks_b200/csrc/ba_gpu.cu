@@ -233,6 +233,8 @@ struct Impl : ba_handle {
   DevBuf<int> d_view, d_point, d_pt_start, d_tile_pt, d_info;
   DevBuf<int> d_slot, d_cam_start, d_blk_a, d_blk_b, d_blk_start, d_blk_order, d_counter;  // static structure of the deterministic Schur gather
   DevBuf<int2> d_pairs;
+  DevBuf<int> d_unit_pt, d_big_pt;  // warp units (points with <= 32 observations) / tiles of the larger points
+  int nunits = 0, nbig = 0;
   DevBuf<T> d_P, d_Q, d_Pt;  // per-observation / per-point records written by k_point_factor
   int nblocks = 0, gather_grid = 0;
   DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g */, d_keep, d_y, d_dvec, d_tmp;
@@ -311,6 +313,18 @@ struct Impl : ba_handle {
     tile_pt.push_back(M);
     ntiles = (int)tile_pt.size() - 1;
 
+    // point factor work units: one warp per run of consecutive points whose observations fit 32 lanes
+    // (k_point_factor_warp); a point with more than 32 observations becomes its own shared-memory tile
+    std::vector<int> unit_pt, big_pt;
+    for (int j = 0; j < M;) {
+      const int nj = pt_start[j + 1] - pt_start[j];
+      if (nj > 32) { big_pt.push_back(j); big_pt.push_back(j + 1); ++j; continue; }
+      int j1 = j, cnt = 0;
+      while (j1 < M && pt_start[j1 + 1] - pt_start[j1] <= 32 && cnt + (pt_start[j1 + 1] - pt_start[j1]) <= 32) { cnt += pt_start[j1 + 1] - pt_start[j1]; ++j1; }
+      unit_pt.push_back(j); unit_pt.push_back(j1);
+      j = j1;
+    }
+    nunits = (int)unit_pt.size() / 2; nbig = (int)big_pt.size() / 2;
     // static structure of the Schur gather: camera-major record slots, non-empty camera-pair blocks, pair lists
     std::vector<int> cam_start(N + 1, 0), slot(K);
     for (int i = 0; i < K; ++i) cam_start[view[i] + 1]++;
@@ -369,6 +383,9 @@ struct Impl : ba_handle {
     CK(cudaMemcpyAsync(d_point.p, point, K * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_pt_start.p, pt_start.data(), (M + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_tile_pt.p, tile_pt.data(), (ntiles + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(d_unit_pt.alloc(unit_pt.size())); CK(d_big_pt.alloc(big_pt.size()));
+    if (nunits) CK(cudaMemcpyAsync(d_unit_pt.p, unit_pt.data(), unit_pt.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (nbig) CK(cudaMemcpyAsync(d_big_pt.p, big_pt.data(), big_pt.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(d_slot.alloc(K)); CK(d_cam_start.alloc(N + 1)); CK(d_blk_a.alloc(nblocks)); CK(d_blk_b.alloc(nblocks)); CK(d_blk_start.alloc(nblocks + 1));
     CK(d_blk_order.alloc(nblocks)); CK(d_counter.alloc(1));
     CK(cudaMemcpyAsync(d_blk_order.p, blk_order.data(), nblocks * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -554,8 +571,11 @@ struct Impl : ba_handle {
     const T diag = (variant == BA_CHOLESKY) ? lamT : sl * sl;  // QR variants square the sqrt(lambda) rows
     mark(0);
     CK(cudaMemsetAsync(d_red.p, 0, (red_count + 2 * (size_t)n) * sizeof(T), stream));
-    k_point_factor<T><<<ntiles, TILE, sizeof(TileSmem<T>), stream>>>(tile_args(lamT), d_slot.p, d_P.p, d_Q.p, d_Pt.p);
-    launches++;
+    if (nunits) { k_point_factor_warp<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, 0, stream>>>(tile_args(lamT), nunits, d_unit_pt.p, d_slot.p, d_P.p, d_Q.p, d_Pt.p); launches++; }
+    if (nbig) {
+      TileArgs<T> ab = tile_args(lamT); ab.tile_pt = d_big_pt.p;
+      k_point_factor<T><<<nbig, TILE, sizeof(TileSmem<T>), stream>>>(ab, 2, d_slot.p, d_P.p, d_Q.p, d_Pt.p); launches++;
+    }
     CK(cudaGetLastError());
     mark(1);
     CK(cudaMemsetAsync(d_counter.p, 0, sizeof(int), stream));

@@ -312,12 +312,12 @@ __device__ __forceinline__ void load4(const float* p, float& a, float& b, float&
 }
 
 template <class T>
-__global__ void __launch_bounds__(TILE) k_point_factor(TileArgs<T> a, const int* __restrict__ slot, T* __restrict__ Prec, T* __restrict__ Qrec,
-                                                       T* __restrict__ Ptrec) {
+__global__ void __launch_bounds__(TILE) k_point_factor(TileArgs<T> a, const int stride, const int* __restrict__ slot, T* __restrict__ Prec,
+                                                       T* __restrict__ Qrec, T* __restrict__ Ptrec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<T>& sm = *reinterpret_cast<TileSmem<T>*>(smem_raw);
   const int t = threadIdx.x, tile = blockIdx.x;
-  const int p0 = a.tile_pt[tile], p1 = a.tile_pt[tile + 1], npts = p1 - p0;
+  const int p0 = a.tile_pt[stride * tile], p1 = a.tile_pt[stride * tile + 1], npts = p1 - p0;  // stride 2: (first, end) pairs
   const int o0 = a.pt_start[p0], nobs = a.pt_start[p1] - o0;
   int cam_idx, lp;
   tile_phases_123<T>(a, sm, t, p0, npts, o0, nobs, cam_idx, lp);
@@ -356,6 +356,237 @@ __global__ void __launch_bounds__(TILE) k_point_factor(TileArgs<T> a, const int*
     store4(q + 4, sm.Rm[4 * TP + t], sm.Rm[5 * TP + t], sm.C[t], sm.C[TP + t]);
     store4(q + 8, sm.C[2 * TP + t], sm.G[t], sm.G[TP + t], sm.G[2 * TP + t]);
     store4(q + 12, (T)sm.perm[t], T(0), T(0), T(0));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-segmented point factor: one WARP per unit of consecutive points whose observations fit 32 lanes,
+// lane = observation, everything in registers. A point's rows live in the lanes of its segment; sums
+// over a point (column norms, reflector dots, Q1^T e, Jp^T e, normal equations) are segmented sums done
+// with shuffles in row order (every lane of the segment computes the identical value, so the 3x3 R,
+// the reflector scalars and the sqrt(lambda) I3 rows are simply replicated in the segment's lanes).
+// No shared memory, no block barriers: the tile version (k_point_factor, kept for points with more than
+// 32 observations) spends most of its time in one-lane-per-point loops over shared memory behind
+// __syncthreads (ncu: barrier stall 17.7 per issue, 9 % issue utilisation).
+// ---------------------------------------------------------------------------------------------
+template <class T, int NV>
+__device__ __forceinline__ void seg_sum(T (&v)[NV], const int s0, const int n, const int nmax) {
+  T acc[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) acc[q] = T(0);
+  for (int t = 0; t < nmax; ++t) {
+    const int src = (s0 + t) & 31;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) { const T o = __shfl_sync(0xffffffffu, v[q], src); if (t < n) acc[q] += o; }
+  }
+#pragma unroll
+  for (int q = 0; q < NV; ++q) v[q] = acc[q];
+}
+template <class T> __device__ __forceinline__ void cswap(T& a, T& b, bool sw) { const T t = a; a = sw ? b : a; b = sw ? t : b; }
+
+// x[a][c]: the lane's two rows of Jp (row 2i+a of the point block); on return the thin Q1 rows.
+template <class T>
+__device__ __forceinline__ void seg_householder(T (&x)[2][3], const T e0, const T e1, const T sl, const int s0, const int n, const int i,
+                                                const int nmax, T (&R)[6], int& pm, T (&cq)[3]) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const T tiny = (sizeof(T) == 8 ? T(2.2250738585072014e-308) : T(1.17549435e-38f));
+  T L[3][3] = {{sl, T(0), T(0)}, {T(0), sl, T(0)}, {T(0), T(0), sl}};
+  T tau[3];
+  int pmv[3] = {0, 1, 2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const bool ge0 = 2 * i >= k, ge1 = 2 * i + 1 >= k, gt0 = 2 * i > k, gt1 = 2 * i + 1 > k;
+    const int own = (s0 + (k >> 1)) & 31;  // lane holding row k, in slot k & 1
+    // squared norms of the remaining columns over rows >= k (pivot rule)
+    T nn[3] = {T(0), T(0), T(0)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c >= k) nn[c] = (ge0 ? x[0][c] * x[0][c] : T(0)) + (ge1 ? x[1][c] * x[1][c] : T(0));
+    seg_sum<T, 3>(nn, s0, n, nmax);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c >= k) nn[c] += L[0][c] * L[0][c] + L[1][c] * L[1][c] + L[2][c] * L[2][c];
+    int best = k;
+    T bestv = nn[k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c > k && nn[c] > bestv) { best = c; bestv = nn[c]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c > k) {
+        const bool sw = best == c;
+        cswap(x[0][k], x[0][c], sw); cswap(x[1][k], x[1][c], sw);
+        cswap(L[0][k], L[0][c], sw); cswap(L[1][k], L[1][c], sw); cswap(L[2][k], L[2][c], sw);
+        const int t = pmv[k]; pmv[k] = sw ? pmv[c] : pmv[k]; pmv[c] = sw ? t : pmv[c];
+      }
+    }
+    const T c0 = __shfl_sync(FULL, (k & 1) ? x[1][k] : x[0][k], own);
+    T t2[1] = {(gt0 ? x[0][k] * x[0][k] : T(0)) + (gt1 ? x[1][k] * x[1][k] : T(0))};
+    seg_sum<T, 1>(t2, s0, n, nmax);
+    const T tail2 = t2[0] + L[0][k] * L[0][k] + L[1][k] * L[1][k] + L[2][k] * L[2][k];
+    const bool degenerate = tail2 <= tiny;
+    T beta = tsqrt(c0 * c0 + tail2);
+    if (c0 >= T(0)) beta = -beta;
+    if (degenerate) beta = c0;
+    const T inv = degenerate ? T(0) : T(1) / (c0 - beta);
+    const T tk = degenerate ? T(0) : (beta - c0) / beta;
+    if (gt0) x[0][k] *= inv;
+    if (gt1) x[1][k] *= inv;
+    L[0][k] *= inv; L[1][k] *= inv; L[2][k] *= inv;
+    tau[k] = tk;
+    const bool mine = (i == (k >> 1));
+    if (mine) { if (k & 1) x[1][k] = beta; else x[0][k] = beta; }
+    // apply H_k to the remaining columns
+    T dots[2] = {T(0), T(0)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c > k) dots[c - k - 1] = (gt0 ? x[0][k] * x[0][c] : T(0)) + (gt1 ? x[1][k] * x[1][c] : T(0));
+    if (k < 2) seg_sum<T, 2>(dots, s0, n, nmax);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c > k) {
+        const T akc = __shfl_sync(FULL, (k & 1) ? x[1][c] : x[0][c], own);
+        T sdot = akc + dots[c - k - 1] + L[0][k] * L[0][c] + L[1][k] * L[1][c] + L[2][k] * L[2][c];
+        sdot *= tk;
+        if (mine) { if (k & 1) x[1][c] -= sdot; else x[0][c] -= sdot; }
+        if (gt0) x[0][c] -= sdot * x[0][k];
+        if (gt1) x[1][c] -= sdot * x[1][k];
+        L[0][c] -= sdot * L[0][k]; L[1][c] -= sdot * L[1][k]; L[2][c] -= sdot * L[2][k];
+      }
+    }
+  }
+  // R sits in rows 0..2 (lane s0: rows 0, 1; lane s0+1: row 2), already in pivoted column order
+  const int l0 = s0 & 31, l1 = (s0 + 1) & 31;
+  R[0] = __shfl_sync(FULL, x[0][0], l0); R[1] = __shfl_sync(FULL, x[0][1], l0); R[2] = __shfl_sync(FULL, x[0][2], l0);
+  R[3] = __shfl_sync(FULL, x[1][1], l0); R[4] = __shfl_sync(FULL, x[1][2], l0); R[5] = __shfl_sync(FULL, x[0][2], l1);
+  pm = pmv[0] | (pmv[1] << 2) | (pmv[2] << 4);
+  // form the thin Q1 in place (dorg2r): k = 2, 1, 0
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    const bool gt0 = 2 * i > k, gt1 = 2 * i + 1 > k, lt0 = 2 * i < k, lt1 = 2 * i + 1 < k;
+    const int own = (s0 + (k >> 1)) & 31;
+    const bool mine = (i == (k >> 1));
+    const T tk = tau[k];
+    T dots[2] = {T(0), T(0)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c > k) dots[c - k - 1] = (gt0 ? x[0][k] * x[0][c] : T(0)) + (gt1 ? x[1][k] * x[1][c] : T(0));
+    if (k < 2) seg_sum<T, 2>(dots, s0, n, nmax);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c > k) {
+        const T akc = __shfl_sync(FULL, (k & 1) ? x[1][c] : x[0][c], own);
+        T sdot = akc + dots[c - k - 1] + L[0][k] * L[0][c] + L[1][k] * L[1][c] + L[2][k] * L[2][c];
+        sdot *= tk;
+        if (mine) { if (k & 1) x[1][c] -= sdot; else x[0][c] -= sdot; }
+        if (gt0) x[0][c] -= sdot * x[0][k];
+        if (gt1) x[1][c] -= sdot * x[1][k];
+        L[0][c] -= sdot * L[0][k]; L[1][c] -= sdot * L[1][k]; L[2][c] -= sdot * L[2][k];
+      }
+    }
+    if (gt0) x[0][k] *= -tk;
+    if (gt1) x[1][k] *= -tk;
+    L[0][k] *= -tk; L[1][k] *= -tk; L[2][k] *= -tk;
+    if (mine) { if (k & 1) x[1][k] = T(1) - tk; else x[0][k] = T(1) - tk; }
+    if (lt0) x[0][k] = T(0);
+    if (lt1) x[1][k] = T(0);
+  }
+  cq[0] = x[0][0] * e0 + x[1][0] * e1; cq[1] = x[0][1] * e0 + x[1][1] * e1; cq[2] = x[0][2] * e0 + x[1][2] * e1;
+  seg_sum<T, 3>(cq, s0, n, nmax);
+}
+
+// Normal-equation point factor (CHOLESKY variant; single-observation points): V = Jp^T Jp + lambda I = L D L^T,
+// R := D^{1/2} L^T, Q1 rows := Jp rows * R^{-1}.
+template <class T>
+__device__ __forceinline__ void seg_normal(T (&x)[2][3], const T e0, const T e1, const T lambda, const int s0, const int n, const int nmax,
+                                           T (&R)[6], int& pm, T (&cq)[3]) {
+  T v[6] = {x[0][0] * x[0][0] + x[1][0] * x[1][0], x[0][1] * x[0][0] + x[1][1] * x[1][0], x[0][1] * x[0][1] + x[1][1] * x[1][1],
+            x[0][2] * x[0][0] + x[1][2] * x[1][0], x[0][2] * x[0][1] + x[1][2] * x[1][1], x[0][2] * x[0][2] + x[1][2] * x[1][2]};
+  seg_sum<T, 6>(v, s0, n, nmax);
+  const T v00 = v[0] + lambda, v10 = v[1], v11 = v[2] + lambda, v20 = v[3], v21 = v[4], v22 = v[5] + lambda;
+  const T d0 = v00, l10 = v10 / d0, l20 = v20 / d0;
+  const T d1 = v11 - l10 * l10 * d0, l21 = (v21 - l20 * l10 * d0) / d1;
+  const T d2 = v22 - l20 * l20 * d0 - l21 * l21 * d1;
+  const T q0 = tsqrt(d0), q1 = tsqrt(d1), q2 = tsqrt(d2);
+  R[0] = q0; R[1] = q0 * l10; R[2] = q0 * l20; R[3] = q1; R[4] = q1 * l21; R[5] = q2;
+  pm = 0 | (1 << 2) | (2 << 4);
+  const T i00 = T(1) / R[0], i11 = T(1) / R[3], i22 = T(1) / R[5];
+#pragma unroll
+  for (int a2 = 0; a2 < 2; ++a2) {
+    const T y0 = x[a2][0] * i00;
+    const T y1 = (x[a2][1] - y0 * R[1]) * i11;
+    const T y2 = (x[a2][2] - y0 * R[2] - y1 * R[4]) * i22;
+    x[a2][0] = y0; x[a2][1] = y1; x[a2][2] = y2;
+  }
+  cq[0] = x[0][0] * e0 + x[1][0] * e1; cq[1] = x[0][1] * e0 + x[1][1] * e1; cq[2] = x[0][2] * e0 + x[1][2] * e1;
+  seg_sum<T, 3>(cq, s0, n, nmax);
+}
+
+template <class T>
+__global__ void __launch_bounds__(TILE) k_point_factor_warp(TileArgs<T> a, int nunits, const int* __restrict__ unit_pt, const int* __restrict__ slot,
+                                                            T* __restrict__ Prec, T* __restrict__ Qrec, T* __restrict__ Ptrec) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, u = blockIdx.x * (TILE / 32) + (threadIdx.x >> 5);
+  if (u >= nunits) return;
+  const int p0 = __ldg(unit_pt + 2 * u), p1 = __ldg(unit_pt + 2 * u + 1);
+  const int o0 = __ldg(a.pt_start + p0), un = __ldg(a.pt_start + p1) - o0;
+  const bool act = lane < un;
+  const int o = o0 + (act ? lane : 0);
+  const int cam_idx = __ldg(a.view + o), pj = __ldg(a.point + o);
+  int s0 = lane, n = 1;
+  if (act) { const int ps = __ldg(a.pt_start + pj); s0 = ps - o0; n = __ldg(a.pt_start + pj + 1) - ps; }
+  const int i = lane - s0;
+  Cam<T> c; load_cam<T>(a.cams, cam_idx, c);
+  const T X0 = __ldg(a.X + 3 * (size_t)pj), X1 = __ldg(a.X + 3 * (size_t)pj + 1), X2 = __ldg(a.X + 3 * (size_t)pj + 2);
+  const T m0 = __ldg(a.meas + 2 * (size_t)o), m1 = __ldg(a.meas + 2 * (size_t)o + 1);
+  T e0, e1, jc[18], jp[6];
+  obs_jacobian<T>(c, X0, X1, X2, m0, m1, a.tau2, e0, e1, jc, jp);
+  T x[2][3] = {{jp[0], jp[1], jp[2]}, {jp[3], jp[4], jp[5]}};
+  if (!act) {
+    e0 = e1 = T(0);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { x[0][q] = T(0); x[1][q] = T(0); }
+  }
+  const int nmax = __reduce_max_sync(FULL, n);
+  T G[3] = {x[0][0] * e0 + x[1][0] * e1, x[0][1] * e0 + x[1][1] * e1, x[0][2] * e0 + x[1][2] * e1};
+  seg_sum<T, 3>(G, s0, n, nmax);
+  const bool use_h = (a.factor == PF_HOUSEHOLDER) && n >= 2;
+  T R[6], cq[3]; int pm = 0;
+  T xh[2][3], Rh[6], ch[3]; int pmh = 0;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { xh[0][q] = x[0][q]; xh[1][q] = x[1][q]; }
+  if (__any_sync(FULL, use_h)) seg_householder<T>(xh, e0, e1, tsqrt(a.lambda), s0, n, i, nmax, Rh, pmh, ch);
+  if (__any_sync(FULL, !use_h)) seg_normal<T>(x, e0, e1, a.lambda, s0, n, nmax, R, pm, cq);
+  if (use_h) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { x[0][q] = xh[0][q]; x[1][q] = xh[1][q]; cq[q] = ch[q]; }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) R[q] = Rh[q];
+    pm = pmh;
+  }
+  if (!act) return;
+  const size_t sl = (size_t)__ldg(slot + o);
+  T* pr = Prec + sl * REC;
+  T* qr = Qrec + sl * REC;
+  T gob[9];
+#pragma unroll
+  for (int b = 0; b < 9; ++b) gob[b] = jc[b] * e0 + jc[9 + b] * e1;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      T r12[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) { const int b = 3 * g + q; r12[q] = x[0][k] * jc[b] + x[1][k] * jc[9 + b]; gob[b] -= r12[q] * cq[k]; }
+      store4(pr + 12 * k + 4 * g, r12[0], r12[1], r12[2], T(0));
+    }
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int g = 0; g < 3; ++g) store4(qr + 12 * r + 4 * g, jc[9 * r + 3 * g], jc[9 * r + 3 * g + 1], jc[9 * r + 3 * g + 2], r == 0 ? e0 : e1);
+#pragma unroll
+  for (int g = 0; g < 3; ++g) store4(qr + 24 + 4 * g, gob[3 * g], gob[3 * g + 1], gob[3 * g + 2], T(0));
+  if (i == 0) {
+    T* q = Ptrec + (size_t)pj * PREC;
+    store4(q, R[0], R[1], R[2], R[3]);
+    store4(q + 4, R[4], R[5], cq[0], cq[1]);
+    store4(q + 8, cq[2], G[0], G[1], G[2]);
+    store4(q + 12, (T)pm, T(0), T(0), T(0));
   }
 }
 

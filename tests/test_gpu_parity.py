@@ -207,6 +207,28 @@ def test_edge_cases_gpu():
     dxn, _, et = s.solve_try()
     assert relv(et, o.energy_at(dxo)) < 1e-9
     s.close()
+    # points with more than 32 observations take the shared-memory tile kernel, the rest the warp-segmented one:
+    # mixed problem (n_j = 2 + Poisson(28) over a 41-camera window), all four variants against the oracle
+    pb = bal.synthetic(48, 400, seed=9, mean_obs=30.0, window=20)
+    counts = np.bincount(pb.point)
+    assert counts.max() > 32 and counts.min() <= 32
+    ob = Oracle(pb)
+    eb, cn2b, cnb = ob.linearize()
+    for variant in VARIANTS:
+        sb = solver.GpuSolver(pb, variant)
+        sb.keep_reduced(True)
+        sb.linearize()
+        lamb = 1e-6 * cnb if variant == "MOREQR" else 1e-12 * cn2b
+        if variant == "MOREQR":
+            ob.moreqr_outer()
+        okb, dxb = ob.step(solver.VARIANTS[variant], lamb)
+        So, go = ob.reduced()
+        sb.compute(lamb)
+        dxnb, _, etb = sb.solve_try()
+        Sg, gg = sb.reduced()
+        assert rel(Sg, So) < 1e-11
+        assert relv(etb, ob.energy_at(dxb)) < 1e-9
+        sb.close()
     # rejected input: unsorted / duplicate observations, too many observations on one point
     bad = p.copy(); bad.view = p.view[::-1].copy(); bad.point = p.point[::-1].copy()
     with pytest.raises(solver.BAError):
