@@ -518,7 +518,7 @@ __device__ __forceinline__ void seg_normal(T (&x)[2][3], const T e0, const T e1,
 }
 
 template <class T>
-__global__ void __launch_bounds__(TILE) k_point_factor_warp(TileArgs<T> a, int nunits, const int* __restrict__ unit_pt, const int* __restrict__ slot,
+__global__ void __launch_bounds__(TILE, 4) k_point_factor_warp(TileArgs<T> a, int nunits, const int* __restrict__ unit_pt, const int* __restrict__ slot,
                                                             T* __restrict__ Prec, T* __restrict__ Qrec, T* __restrict__ Ptrec) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, u = blockIdx.x * (TILE / 32) + (threadIdx.x >> 5);
