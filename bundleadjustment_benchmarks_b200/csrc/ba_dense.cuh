@@ -511,6 +511,15 @@ __device__ __forceinline__ void frag_rc(int gt, int e, int& r, int& c) {
   }
 }
 
+// One band system per cluster (grid = nclusters x cluster size). The forward part factors panels [0, np_fwd) only
+// (their updates still flow into the rows below: the Schur complement onto the remaining rows), the backward part
+// starts at panel kb_bwd - 1 with y given for the rows of the tiles >= kb_bwd. A whole system is np_fwd = kb_bwd =
+// number of tiles; the partial forms serve the two-sided factorisation (ba_gpu.cu).
+template <class T> struct LdltProblem {
+  BandMat<T> A; T* dvec; T* Wbuf; T* rhs; T* y; int* info; int np_fwd; int kb_bwd; int do_fwd; int do_bwd;
+};
+template <class T> struct LdltJob { LdltProblem<T> p[2]; T sign; };
+
 // Kernel. Two teams of 4 warps per CTA:
 //   chain team (warps 0-3): per panel k stages the diagonal tile, warp 0 factors it (every CTA redundantly),
 //     warps 1-3 solve the CTA's row tiles (and form W_k); then joins the update team.
@@ -521,10 +530,14 @@ __device__ __forceinline__ void frag_rc(int gt, int e, int& r, int& c) {
 //     tile-ops of a phase are handed out per CTA through a shared-memory counter, so the chain team picks
 //     up whatever is left when it is done.
 template <class T>
-__global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> A, T* __restrict__ dvec, T* Wbuf,
-                                                                      T* rhs, T* y, T sign, int* __restrict__ info, long long* __restrict__ dbg) {
+__global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJob<T> job, long long* __restrict__ dbg, int roww_arg) {
   using V2 = typename VecOf<T>::V2;
   cg::cluster_group cluster = cg::this_cluster();
+  const LdltProblem<T>& P = job.p[blockIdx.x / cluster.num_blocks()];
+  const BandMat<T> A = P.A;
+  T* const dvec = P.dvec; T* const Wbuf = P.Wbuf; T* const rhs = P.rhs; T* const y = P.y; int* const info = P.info;
+  const T sign = job.sign;
+  const int np_fwd = P.np_fwd, kb_bwd = P.kb_bwd;
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int EPC = 16 / (int)sizeof(T);   // elements per 16-byte chunk
   constexpr int CPR = NB / EPC;              // chunks per tile row
@@ -546,8 +559,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
   // the register factorisation took 6.4 us instead of 2.7 us per panel next to an update team, profiles/)
   // row tiles live on the six warps that do not share an SMSP with the factoring warp 0 (warps 1-3, 5-7);
   // warp 4 (same SMSP as warp 0) only forms W_k, after the factorisation
-  constexpr int ROWW = CL_WARPS - 2;
-  const int NC = min(max(1, C / 4), (bt + ROWW - 1) / ROWW);
+  const int ROWW = (roww_arg == 3) ? 3 : CL_WARPS - 2;  // 3: warps 1-3 only (one row warp per SMSP, more chain CTAs)
+  const int NC = min(max(1, (ROWW == 3) ? C / 2 : C / 4), (bt + ROWW - 1) / ROWW);
   int* const work0 = cluster.map_shared_rank(&sm.work[0], 0);
 #ifdef BA_DENSE_TICKS
 #define TICK(i) { if (threadIdx.x == 128) { const long long t1_ = clock64(); sm.tc[i] += t1_ - t0; t0 = t1_; } __syncwarp(); }
@@ -620,7 +633,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
     // fetched (and updated) while the diagonal tile is factored.
     T a[NB];
     const bool w_warp = (warp == 4) && (rank == k % NC);
-    const bool row_warp = (warp & 3) != 0;
+    const bool row_warp = (warp & 3) != 0 && (ROWW == 6 || warp < 4);
     const int ri = (warp < 4) ? warp - 1 : warp - 2;  // 0..5 over warps 1,2,3,5,6,7
     int it = row_warp ? k + 1 + rank + NC * ri : last + 1;
     bool pre = row_warp && (it <= last);
@@ -793,15 +806,18 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
     };
     int slot = 0, buf = 0, bi = 0, bj = 0;
     int* const wk = work0 + (k & 1);
-    if (gt == 0) sm.grab[team][0] = atomicAdd(wk, 1);
+    // the counter lives in CTA 0 (DSMEM atomics, ~0.3 us round trip): items are fetched TWO ahead so that the
+    // round trip never sits between two block-ops
+    if (gt == 0) { sm.grab[team][0] = atomicAdd(wk, 1); sm.grab[team][1] = atomicAdd(wk, 1); }
     group_barrier(team);
     int p = sm.grab[team][0];
+    int pn = sm.grab[team][1];
     if (p < count) { decode(p, bi, bj); stage_block(0, bi, bj); }
     const int lr = lane >> 2, lc = lane & 3;
     while (p < count) {
       const int ci = k + 2 + 2 * bi + (tw >> 1), cj = k + 2 + 2 * bj + (tw & 1);  // this warp's tile
-      slot ^= 1;
-      if (gt == 0) sm.grab[team][slot] = atomicAdd(wk, 1);
+      int gnext = 0;
+      if (gt == 0 && pn < count) gnext = atomicAdd(wk, 1);  // item after next (in flight during this block-op)
       // C fragments straight into the accumulators (in flight while the operands land)
       const bool active = ci <= last && cj <= ci && (ci - cj) * NB - (NB - 1) <= kd;
       const bool interior = active && (ci != cj) && (ci * NB + NB - 1 < n) && (ci * NB + NB - 1 - cj * NB <= kd);
@@ -825,7 +841,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
       }
       cp_async_wait_all();
       group_barrier(team);  // operands landed; next item visible; everyone is done with the other buffer
-      p = sm.grab[team][slot];
+      p = pn;
       if (p < count) { decode(p, bi, bj); stage_block(buf ^ 1, bi, bj); }
       if (active) {
         T acc[32];
@@ -850,7 +866,46 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
           }
         }
       }
+      // hand the prefetched item index to the team (read after the next iteration's barrier)
+      slot ^= 1;
+      if (gt == 0) sm.grab[team][slot] = (pn < count) ? gnext : count;
+      group_barrier(team);
+      pn = sm.grab[team][slot];
       buf ^= 1;
+    }
+  };
+
+  // ---- partial factorisation only: the tiles (i, k+1) get panel k's update outside a chain (one warp per tile,
+  // plain loads; runs once per problem)
+  auto col_phase = [&](const int k) {
+    const int k0 = k * NB, last = min(nt - 1, k + bt), nb = last - k;
+    if (tid < NB) sm.sdU[k & 1][tid] = dvec[k0 + tid];
+    __syncthreads();
+    const T* sd = sm.sdU[k & 1];
+    T (*tiles)[NB][TS] = reinterpret_cast<T (*)[NB][TS]>(&sm.gA[0][0][0][0][0]);  // 8 + 8 tile slots (gA, gB)
+    T (&bufA)[NB][TS] = tiles[warp];
+    T (&bufB)[NB][TS] = tiles[CL_WARPS + warp];
+    const int lr = lane >> 2, lc = lane & 3;
+    for (int p = rank * CL_WARPS + warp; p < nb; p += C * CL_WARPS) {
+      const int ti = k + 1 + p, tj = k + 1;
+      const int ga = ti * NB + lane, gb = tj * NB + lane;
+      for (int c = 0; c < NB; ++c) {
+        const bool oka = ga < n && ga - (k0 + c) <= kd, okb = gb < n && gb - (k0 + c) <= kd;
+        bufA[lane][c] = *(oka ? Av + (size_t)ga * lds + k0 + c : zp);
+        bufB[lane][c] = *(okb ? Av + (size_t)gb * lds + k0 + c : zp);
+      }
+      __syncwarp();
+      T acc[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) acc[e] = T(0);
+      block_mma(bufA, bufB, sd, lane, acc);
+      T* cp = Av + (size_t)(ti * NB) * lds + tj * NB;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int r = (e >> 3) * 8 + lr, c = ((e >> 1) & 3) * 8 + 2 * lc + (e & 1), gi = ti * NB + r, gj = tj * NB + c;
+        if (gi < n && gj <= gi && gi - gj <= kd) cp[r * lds + c] += acc[e];
+      }
+      __syncwarp();
     }
   };
 
@@ -858,20 +913,27 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
   // Iteration k: chain(k+1) (which first gives column k+1 panel k's update) runs next to the update of
   // the columns >= k+2 with panel k; the chain team joins the update when it is done.
   __syncthreads();
-  if (rank < NC) chain(0);
-  cluster.sync();
-  for (int k = 0; k < nt; ++k) {
-    TICK(1)
-    if (tid < NB) sm.sdU[k & 1][tid] = dvec[k * NB + tid];        // D_k (published by rank 0) for the updates
-    if (rank == 0 && tid == 0) sm.work[(k + 1) & 1] = 0;          // next panel's counter (idle during this one)
-    __syncthreads();
-    if (rank < NC && k + 1 < nt) chain(k + 1);
-    TICK(2)
-    block_phase(k);
-    TICK(3)
+  if (P.do_fwd) {
+    if (rank < NC && np_fwd > 0) chain(0);
     cluster.sync();
-    TICK(4)
+    for (int k = 0; k < np_fwd; ++k) {
+      TICK(1)
+      if (tid < NB) sm.sdU[k & 1][tid] = dvec[k * NB + tid];        // D_k (published by rank 0) for the updates
+      if (rank == 0 && tid == 0) sm.work[(k + 1) & 1] = 0;          // next panel's counter (idle during this one)
+      __syncthreads();
+      if (rank < NC && k + 1 < np_fwd) chain(k + 1);
+      TICK(2)
+      block_phase(k);
+      TICK(3)
+      cluster.sync();
+      TICK(4)
+    }
+    if (np_fwd < nt) {  // partial factorisation: the first remaining column still owes panel np_fwd-1's update
+      col_phase(np_fwd - 1);
+      cluster.sync();
+    }
   }
+  if (!P.do_bwd) return;
   // ------------------------------------------------------------------ backward pass, whole cluster
   T* slots = &sm.gA[0][0][0][0][0];                    // [2][bt][NB] far-tile partial sums, written through DSMEM
   T* slots0 = cluster.map_shared_rank(slots, 0);    // CTA 0's copy
@@ -910,10 +972,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
       if (warp == 4) sm.sw[p][lane] = *((km0 + lane < n) ? rhs + km0 + lane : zp);
     }
   };
-  stage(nt - 1);
+  stage(kb_bwd - 1);
   cluster.sync();
-  T yprev = T(0);
-  for (int k = nt - 1; k >= 0; --k) {
+  T yprev = (rank == 0 && warp == 0 && kb_bwd < nt && kb_bwd * NB + lane < n) ? sign * y[kb_bwd * NB + lane] : T(0);
+  for (int k = kb_bwd - 1; k >= 0; --k) {
     if (rank == 0 && warp == 0) {
       const int p = k & 1, k0 = k * NB;
       const int nfar = min(nt - 1, k + bt) - (k + 2) + 1;
@@ -944,6 +1006,41 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(BandMat<T> 
   if (dbg && rank == 0 && tid == 128) for (int i = 0; i < 16; ++i) dbg[i] = sm.tc[i];
 #undef TICK
 #undef TICKC
+}
+
+// ---- helpers of the two-sided factorisation (ba_gpu.cu): the bottom part of S is eliminated from the last row
+// upwards, i.e. as an ordinary top-down factorisation of the index-reversed matrix S'(i', j') = S(n-1-j', n-1-i').
+// rows0 = first row of S that S' covers (S' has np = n - rows0 rows); the block of the rows >= mrow0 of S' (the
+// middle block, which both eliminations update) starts from zero and is added to S afterwards.
+template <class T>
+__global__ void k_band_reverse(BandMat<T> A, const T* __restrict__ g, T* __restrict__ Rv, T* __restrict__ gr, int np, int mrow0) {
+  const int n = A.n, kd = A.kd;
+  const size_t lds = A.lds, total = (size_t)np * (kd + 1), stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int ip = (int)(idx / (kd + 1)), d = (int)(idx - (size_t)ip * (kd + 1)), jp = ip - d;
+    if (jp < 0) continue;
+    T v = T(0);
+    if (!(ip >= mrow0 && jp >= mrow0)) v = A.v[(size_t)(n - 1 - jp) * lds + (n - 1 - ip)];
+    Rv[(size_t)ip * lds + jp] = v;
+  }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)np; i += stride) gr[i] = ((int)i < mrow0) ? g[n - 1 - i] : T(0);
+}
+// S(i, j) += S'(n-1-j, n-1-i), g(i) += g'(n-1-i) for the middle rows [r0, r0 + nm)
+template <class T>
+__global__ void k_band_combine(BandMat<T> A, T* __restrict__ g, const T* __restrict__ Rv, const T* __restrict__ gr, int r0, int nm) {
+  const int n = A.n, kd = A.kd;
+  const size_t lds = A.lds, total = (size_t)nm * (kd + 1), stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int i = r0 + (int)(idx / (kd + 1)), d = (int)(idx % (kd + 1)), j = i - d;
+    if (j < r0) continue;
+    A.v[(size_t)i * lds + j] += Rv[(size_t)(n - 1 - j) * lds + (n - 1 - i)];
+  }
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < (size_t)nm; t += stride) g[r0 + t] += gr[n - 1 - (r0 + (int)t)];
+}
+// dst[i] = src[n-1-i] for i in [i0, i1)  (dst and src indexed from their own origins: dst_off/src_off)
+template <class T>
+__global__ void k_flip_copy(T* __restrict__ dst, const T* __restrict__ src, int n, int i0, int i1) {
+  for (int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += gridDim.x * blockDim.x) dst[i] = src[n - 1 - i];
 }
 
 }  // namespace ba

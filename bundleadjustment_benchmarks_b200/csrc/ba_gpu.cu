@@ -240,8 +240,11 @@ struct Impl : ba_handle {
   DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g */, d_keep, d_y, d_dvec, d_tmp;
   DevBuf<T> d_qr;  // general band copy for the Householder QR of S
   DevBuf<T> d_W;   // L_kk^-1 tiles kept by the cluster LDLT for the backward pass
+  DevBuf<T> d_rev, d_dvec2, d_W2, d_y2, d_WM;  // two-sided factorisation: reversed bottom system [S' | g'], its D, W, y; middle W
+  bool two_sided = true;
   int cluster_size = 16;  // non-portable size; falls back to 8 when 16 CTAs of this footprint cannot be co-scheduled
   bool solved_in_factor = false;
+  int ldlt_roww = 6;  // row-tile warps per chain CTA of the cluster LDLT (BA_LDLT_ROWW=3|6)
   DevBuf<double> d_partials, d_scal;
   DevBuf<long long> d_dbg;
   double* h_scal = nullptr;  // pinned
@@ -414,6 +417,8 @@ struct Impl : ba_handle {
     coop_grid = std::max(1, std::min(occ, 2)) * sms;
     if (const char* cs = std::getenv("BA_CLUSTER_SIZE")) cluster_size = std::max(1, std::min(16, atoi(cs)));
     if (std::getenv("BA_FORCE_GRID_LDLT")) force_grid_ldlt = true;
+    if (const char* rw = std::getenv("BA_LDLT_ROWW")) ldlt_roww = atoi(rw) == 3 ? 3 : 6;
+    if (const char* ts = std::getenv("BA_LDLT_TWOSIDED")) two_sided = atoi(ts) != 0;
     CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterSmem<T>)));
     CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     for (; cluster_size > 1; cluster_size /= 2) {  // largest cluster the device can co-schedule
@@ -609,15 +614,60 @@ struct Impl : ba_handle {
       const int nt = (n + NB - 1) / NB, bt = (kd + NB - 1) / NB;
       const double flops = (double)n * kd * kd;
       if (flops < 2e11 && bt <= CL_MAX_BT && !force_grid_ldlt) {
-        // latency-bound regime: one cluster, forward solve folded in, backward solve by CTA 0
+        // latency-bound regime: thread-block clusters, forward solve folded in, backward pass on the cluster
+        auto launch = [&](const LdltJob<T>& job, int nclusters) -> cudaError_t {
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(cluster_size * nclusters); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = sizeof(ClusterSmem<T>); cfg.stream = stream;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr; cfg.numAttrs = 1;
+          launches++;
+          return cudaLaunchKernelEx(&cfg, k_band_ldlt_cluster<T>, job, d_dbg.p, ldlt_roww);
+        };
         if (d_W.n < (size_t)nt * NB * NB) CK(d_W.alloc((size_t)nt * NB * NB));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(cluster_size); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = sizeof(ClusterSmem<T>); cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, k_band_ldlt_cluster<T>, A, d_dvec.p, d_W.p, gvec(), d_dx_cam.p, T(-1), d_info.p, d_dbg.p));
+        const int q = (n - (bt + 2) * NB) / (2 * NB);  // panels eliminated from either end by the two-sided scheme
+        if (!two_sided || q < bt + 2) {
+          LdltJob<T> job = {};
+          job.sign = T(-1);
+          job.p[0] = LdltProblem<T>{A, d_dvec.p, d_W.p, gvec(), d_dx_cam.p, d_info.p, nt, nt, 1, 1};
+          CK(launch(job, 1));
+        } else {
+          // Two-sided (twisted) factorisation: the chain of n dependent pivots is cut in two. Cluster 0 eliminates rows
+          // [0, r0) top-down, cluster 1 rows [r0 + nm, n) bottom-up (= top-down on the index-reversed copy S'); both
+          // leave their Schur complement on the middle block [r0, r0 + nm), nm >= kd + 2 panels, which is summed,
+          // factored and solved by one cluster; the two backward passes then run side by side again.
+          const int r0 = q * NB, nm = n - 2 * q * NB, np = n - r0;          // np rows of S' = bottom + middle
+          const int ntp = (np + NB - 1) / NB, ntm = (nm + NB - 1) / NB;
+          const size_t rev_count = (size_t)np * (ldsv + 1);
+          if (d_rev.n < rev_count + np) CK(d_rev.alloc(rev_count + np));
+          if (d_dvec2.n < (size_t)np + NB) CK(d_dvec2.alloc((size_t)np + NB));
+          if (d_W2.n < (size_t)ntp * NB * NB) CK(d_W2.alloc((size_t)ntp * NB * NB));
+          if (d_y2.n < (size_t)np) CK(d_y2.alloc(np));
+          if (d_WM.n < (size_t)ntm * NB * NB) CK(d_WM.alloc((size_t)ntm * NB * NB));
+          T* Rv = d_rev.p + ldsv; T* gr = d_rev.p + rev_count;
+          BandMat<T> Ar{Rv, lds(), np, kd};
+          BandMat<T> Am{Sv() + (size_t)r0 * ldsv + r0, lds(), nm, std::min(kd, nm - 1)};
+          const int ab = 4 * 148;
+          k_band_reverse<T><<<ab, 256, 0, stream>>>(A, gvec(), Rv, gr, np, q * NB);
+          LdltJob<T> job = {};
+          job.sign = T(-1);
+          job.p[0] = LdltProblem<T>{A, d_dvec.p, d_W.p, gvec(), d_dx_cam.p, d_info.p, q, 0, 1, 0};
+          job.p[1] = LdltProblem<T>{Ar, d_dvec2.p, d_W2.p, gr, d_y2.p, d_info.p, q, 0, 1, 0};
+          CK(launch(job, 2));
+          k_band_combine<T><<<64, 256, 0, stream>>>(A, gvec(), Rv, gr, r0, nm);
+          LdltJob<T> mid = {};
+          mid.sign = T(-1);
+          mid.p[0] = LdltProblem<T>{Am, d_dvec.p + r0, d_WM.p, gvec() + r0, d_dx_cam.p + r0, d_info.p, ntm, ntm, 1, 1};
+          CK(launch(mid, 1));
+          k_flip_copy<T><<<8, 256, 0, stream>>>(d_y2.p, d_dx_cam.p, n, q * NB, np);  // y'(i') = y(n-1-i') on the middle rows
+          job.p[0].do_fwd = 0; job.p[0].do_bwd = 1; job.p[0].kb_bwd = q;
+          job.p[1].do_fwd = 0; job.p[1].do_bwd = 1; job.p[1].kb_bwd = q;
+          CK(launch(job, 2));
+          k_flip_copy<T><<<32, 256, 0, stream>>>(d_dx_cam.p, d_y2.p, n, r0 + nm, n);  // y(i) = y'(n-1-i) on the bottom rows
+          launches += 4;
+          CK(cudaGetLastError());
+        }
         solved_in_factor = true;
       } else {
         T* dv = d_dvec.p; int* info = d_info.p;

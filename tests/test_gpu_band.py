@@ -50,6 +50,27 @@ def test_band_solve_matches_numpy(path):
     s.close()
 
 
+@pytest.mark.parametrize("n,kd", [(2500, 257), (3001, 100), (4100, 548), (1990, 31)])
+def test_band_solve_two_sided(n, kd):
+    """Two-sided (twisted) factorisation: rows eliminated from both ends by two clusters, middle block by one.
+    Ragged sizes (n, n - 2*32*q not multiples of 32), compared with numpy and with the one-sided kernel."""
+    A, g = band_spd(n, kd, 300 + n)
+    ref = np.linalg.solve(A, g)
+    s2 = _solve("QRCHOL", "f64", False)
+    y2 = s2.debug_band_solve(A, g, kd)
+    s2.close()
+    os.environ["BA_LDLT_TWOSIDED"] = "0"
+    try:
+        s1 = _solve("QRCHOL", "f64", False)
+    finally:
+        os.environ.pop("BA_LDLT_TWOSIDED", None)
+    y1 = s1.debug_band_solve(A, g, kd)
+    s1.close()
+    assert np.linalg.norm(y2 - ref) / np.linalg.norm(ref) < 1e-12
+    assert np.linalg.norm(y1 - ref) / np.linalg.norm(ref) < 1e-12
+    assert np.linalg.norm(y2 - y1) / np.linalg.norm(ref) < 1e-12
+
+
 def test_band_solve_indefinite_ldlt():
     """SimplicialLDLT semantics: un-pivoted LDL^T also factors symmetric indefinite matrices (D < 0 allowed)."""
     s = _solve("QRCHOL", "f64", False)
