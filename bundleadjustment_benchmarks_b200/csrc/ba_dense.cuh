@@ -259,6 +259,7 @@ template <class T> struct PanelSmem {
   alignas(16) T sd[NB];
   alignas(16) T sinvd[NB];
   alignas(16) T sz[NB];
+  int progress;                   // columns of L_kk published so far (factor warp -> substitution warps)
 };
 
 template <class T> struct ClusterSmem {
@@ -317,6 +318,16 @@ __device__ __forceinline__ double pivot_rcp(double d) {
 }
 __device__ __forceinline__ float pivot_rcp(float d) { return 1.0f / d; }
 
+__device__ __forceinline__ void st_release_cta(int* p, int v) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta(const int* p) {
+  int v; const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+
 // ---- register-resident 32x32 kernels of the panel chain --------------------------------------------
 // Both are ROLLED loops over blocks of 4 columns with the lane's row window rotated by 4 registers per
 // block, so that all register indices are static while the code stays a few KB: the fully unrolled
@@ -372,10 +383,11 @@ __device__ __forceinline__ void warp_ldlt32(T (&a)[NB], T z, const int lane, Pan
   T dj = __shfl_sync(FULL, a[0], 0);
   T zj = __shfl_sync(FULL, z, 0);
   __syncwarp();
+  // after every block of 4 columns the substitution warps may consume them (they run one block behind)
 #pragma unroll 1
-  for (int jb = 0; jb < NB / 2; jb += 4) ldlt_block4<T, NB>(a, z, dj, zj, lane, jb, sm);
+  for (int jb = 0; jb < NB / 2; jb += 4) { ldlt_block4<T, NB>(a, z, dj, zj, lane, jb, sm); __syncwarp(); if (lane == 0) st_release_cta(&sm.progress, jb + 4); }
 #pragma unroll 1
-  for (int jb = NB / 2; jb < NB; jb += 4) ldlt_block4<T, NB / 2>(a, z, dj, zj, lane, jb, sm);
+  for (int jb = NB / 2; jb < NB; jb += 4) { ldlt_block4<T, NB / 2>(a, z, dj, zj, lane, jb, sm); __syncwarp(); if (lane == 0) st_release_cta(&sm.progress, jb + 4); }
 }
 
 // 4 columns of the substitution X L^T = A, lane = row, a[p] = A(row, jb + p). x_m (scaled by 1/d_m when
@@ -413,9 +425,9 @@ template <class T>
 __device__ __forceinline__ T warp_trsm32(T (&a)[NB], const PanelSmem<T>& sm, T* __restrict__ out, const int ostride, const bool scale, const int mmin) {
   T dot = T(0);
 #pragma unroll 1
-  for (int jb = 0; jb < NB / 2; jb += 4) trsm_block4<T, NB>(a, jb, sm, dot, out, ostride, scale, mmin);
+  for (int jb = 0; jb < NB / 2; jb += 4) { while (ld_acquire_cta(&sm.progress) < jb + 4) {} trsm_block4<T, NB>(a, jb, sm, dot, out, ostride, scale, mmin); }
 #pragma unroll 1
-  for (int jb = NB / 2; jb < NB; jb += 4) trsm_block4<T, NB / 2>(a, jb, sm, dot, out, ostride, scale, mmin);
+  for (int jb = NB / 2; jb < NB; jb += 4) { while (ld_acquire_cta(&sm.progress) < jb + 4) {} trsm_block4<T, NB / 2>(a, jb, sm, dot, out, ostride, scale, mmin); }
   return dot;
 }
 
@@ -626,18 +638,80 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
     T (&sBop)[NB][TS] = sm.gB[0][0][0];            // L(k, k-1): column operand of every column-k update
     T (&wbuf)[NB][TS] = *(reinterpret_cast<T (*)[NB][TS]>(&sm.gA[0][0][0][0][0]) + warp);  // per-warp tile buffer (8 of the 8+8 slots)
     const int lr = lane >> 2, lc = lane & 3;
-    TICKC(13)
-    if (upd && tid < 128) stage_operand(sBop, k, kp0);
-    // row-tile warps: work items of warps 1..7 of the NC chain CTAs are the row tiles it = k+1+u, u = rank + NC*(warp-1)
-    // (+ NC*7 per further pass); the last warp of chain CTA k%NC first forms W_k (identity rows). The first tile is
-    // fetched (and updated) while the diagonal tile is factored.
-    T a[NB];
+    T (*tiles)[NB][TS] = reinterpret_cast<T (*)[NB][TS]>(&sm.gA[0][0][0][0][0]);  // 16 tile slots (gA then gB); slot 8 = sBop
+    auto stage_tile_cta = [&](T (&dst)[NB][TS], const int t, const int c0) {  // tile (t, c0/NB) by the whole CTA
+      const int row0 = t * NB;
+      const bool interior = (row0 + NB - 1 < n) && (row0 + NB - 1 - c0 <= kd);
+      const T* tp = Av + (size_t)row0 * lds + c0;
+      if (interior) {
+#pragma unroll
+        for (int q = 0; q < NB * CPR / CL_THREADS; ++q) { const int id = tid + CL_THREADS * q, r = id / CPR, ch = id % CPR; cp_async16(&dst[r][ch * EPC], tp + r * lds + ch * EPC); }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NB * NB / CL_THREADS; ++q) {
+          const int idx = tid + CL_THREADS * q, r = idx >> 5, c = idx & 31, gi = row0 + r;
+          const bool ok = gi < n && gi - (c0 + c) <= kd;
+          dst[r][c] = *(ok ? tp + r * lds + c : zp);
+        }
+      }
+    };
+    // Column-k tiles of this CTA: item 0 = the diagonal tile (every chain CTA, redundantly), items 1..ROWW = the first
+    // tiles of its row warps. They receive panel k-1's update as 4-warp quadrant DMMA products BEFORE the factorisation
+    // starts (two teams, alternating items), so that no tensor work shares the SM with the pivot chain; results go to
+    // shared memory: the diagonal tile to sL, row tile j to the tile buffer of its row warp.
     const bool w_warp = (warp == 4) && (rank == k % NC);
     const bool row_warp = (warp & 3) != 0 && (ROWW == 6 || warp < 4);
     const int ri = (warp < 4) ? warp - 1 : warp - 2;  // 0..5 over warps 1,2,3,5,6,7
     int it = row_warp ? k + 1 + rank + NC * ri : last + 1;
     bool pre = row_warp && (it <= last);
-    auto fetch_issue = [&](const int t, bool& use_mma) {  // start fetching row tile (t, k): operand + C fragments, or plain rows
+    if (tid == 0) sm.pn.progress = 0;
+    if (upd) {
+      stage_tile_cta(sBop, k, kp0);
+      for (int j = 1; j <= ROWW; ++j) {
+        const int tj = k + 1 + rank + NC * (j - 1);
+        if (tj <= last && tj <= k - 1 + bt) stage_tile_cta(tiles[CL_WARPS + j], tj, kp0);
+      }
+    }
+    cp_async_commit();
+    T cc[4][8];  // C fragments (quadrant layout) of this team's items j = team, team + 2, ...
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = team + 2 * u;
+      const int tj = (j == 0) ? k : k + 1 + rank + NC * (j - 1);
+      const bool have = j <= ROWW && (j == 0 || tj <= last);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int r, c; frag_rc<T>(gt, e, r, c);
+        const int gi = tj * NB + r, gj = k0 + c;
+        const bool ok = have && gi < n && gj <= gi && gi - gj <= kd;
+        cc[u][e] = *(ok ? Av + (size_t)gi * lds + gj : zp);
+      }
+    }
+    const T zr = *((tid < NB && k0 + tid < n) ? rhs + k0 + tid : zp);
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = team + 2 * u;
+      const int tj = (j == 0) ? k : k + 1 + rank + NC * (j - 1);
+      if (j <= ROWW && (j == 0 || tj <= last)) {
+        T dacc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dacc[e] = T(0);
+        if (upd && (j == 0 || tj <= k - 1 + bt)) tile_mma(j == 0 ? sBop : tiles[CL_WARPS + j], sBop, sdp, gt, dacc);
+        const int rw = (j - 1 < 3) ? j : j + 1;  // row warp of item j >= 1: ri = j-1 -> warps 1,2,3,5,6,7
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          int r, c; frag_rc<T>(gt, e, r, c);
+          if (j == 0) sm.sL[r][c] = (k0 + r >= n && r == c) ? T(1) : cc[u][e] + dacc[e];
+          else tiles[rw][r][c] = cc[u][e] + dacc[e];
+        }
+      }
+    }
+    if (tid < NB) sm.pn.sz[tid] = zr;
+    __syncthreads();
+    T a[NB];
+    auto fetch_issue = [&](const int t, bool& use_mma) {  // later passes only: start fetching row tile (t, k)
       use_mma = upd && (t <= k - 1 + bt);
       if (use_mma) {
         stage_tile_warp(wbuf, t, kp0);
@@ -670,36 +744,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
       for (int c = 0; c < NB; ++c) a[c] = wbuf[lane][c];
       __syncwarp();
     };
-    bool pre_mma = false;
-    if (pre) fetch_issue(it, pre_mma);
-    cp_async_commit();
-    // diagonal tile C fragments (quadrant layout of tile_mma)
-    T cc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      int r, c; frag_rc<T>(gt, e, r, c);
-      const int gi = k0 + r, gj = k0 + c;
-      const bool ok = gi < n && c <= r && gi - gj <= kd;
-      cc[e] = *(ok ? Av + (size_t)gi * lds + gj : zp);
-    }
-    const T zr = *((tid < NB && k0 + tid < n) ? rhs + k0 + tid : zp);
-    cp_async_wait_all();
-    __syncthreads();
-    TICKC(8)
-    if (tid < 128) {
-      T dacc[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) dacc[e] = T(0);
-      if (upd) tile_mma(sBop, sBop, sdp, gt, dacc);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        int r, c; frag_rc<T>(gt, e, r, c);
-        sm.sL[r][c] = (k0 + r >= n && r == c) ? T(1) : cc[e] + dacc[e];
-      }
-      if (tid < NB) sm.pn.sz[tid] = zr;
-    }
-    __syncthreads();
-    TICKC(9)
     if (warp == 0) {
       const T z = sm.pn.sz[lane];
 #pragma unroll
@@ -709,12 +753,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
       const T d = sm.pn.sd[lane];
       sm.sdU[k & 1][lane] = d;
       if (rank == 0 && k0 + lane < n && (d == T(0) || !(d == d))) atomicCAS(info, 0, k0 + lane + 1);
-    } else if (pre && pre_mma) {
-      fetch_finish(it);
+    } else if (pre) {
+#pragma unroll
+      for (int c = 0; c < NB; ++c) a[c] = wbuf[lane][c];
+      __syncwarp();
     }
-    TICKC(10)
-    __syncthreads();
-    TICKC(11)
+    // no block barrier here: the substitution warps follow the factorisation one 4-column block behind (sm.pn.progress)
     if (warp == 0 && rank == 0) {  // idle after the factorisation: publish the factored diagonal tile, D and w_k = D^-1 z_k
 #pragma unroll 4
       for (int c = 0; c < NB; ++c) {
@@ -1003,7 +1047,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
     cluster.sync();
   }
   TICK(5)
-  if (dbg && rank == 0 && tid == 128) for (int i = 0; i < 16; ++i) dbg[i] = sm.tc[i];
+  if (dbg && rank == C - 1 && tid == 128) for (int i = 0; i < 8; ++i) dbg[i] = sm.tc[i];   // an update CTA
+  if (dbg && rank == 0 && tid == 32) for (int i = 8; i < 16; ++i) dbg[i] = sm.tc[i];         // a chain CTA's row warp
 #undef TICK
 #undef TICKC
 }

@@ -7,8 +7,8 @@ for _ in range(3):
     s.compute(1e-12 * cn2); s.solve_try(); s.reject()
 s.set_profiling(True); s.compute(1e-12 * cn2); s.solve_try(); s.reject(); print("stage_ms", s.stage_ms())
 c = s.debug_counters()
-names = ["-", "t128: loop top", "t128: (chain skipped)", "t128: block phase", "t128: syncthreads+cluster.sync", "backward(total)", "-", "-",
-         "w1: stage+wait+barrier", "w1: diag tile-op+barrier (idle)", "w1: fetch_finish (row tile update)", "w1: wait for factor", "w1: trsm", "w1: outside chain", "w1: write-out + rhs", "w1: end barrier"]
+names = ["-", "upd CTA: loop top", "upd CTA: (chain skipped)", "upd CTA: block phase", "upd CTA: wait at cluster.sync", "backward(total)", "-", "-",
+         "w1: -", "w1: -", "w1: -", "w1: -", "w1: trsm (incl. waiting for the factor)", "w1: -", "w1: whole chain except trsm", "w1: end barrier + outside"]
 nt = (9 * p.N + 31) // 32
 for n, v in zip(names, c):
     print(f"{n:42s} {v:12d} cycles  = {v/1.9e3:9.1f} us total, {v/1.9e3/nt:6.2f} us/panel")
