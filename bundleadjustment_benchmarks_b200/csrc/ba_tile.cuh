@@ -369,18 +369,21 @@ __global__ void __launch_bounds__(TILE) k_point_factor(TileArgs<T> a, const int 
 // 32 observations) spends most of its time in one-lane-per-point loops over shared memory behind
 // __syncthreads (ncu: barrier stall 17.7 per issue, 9 % issue utilisation).
 // ---------------------------------------------------------------------------------------------
+// Segmented sum over the lanes of a point (segment = lanes s0 .. s0+n-1, i = lane - s0): Hillis-Steele scan with
+// shfl_up restricted to the segment, then the last lane's total is broadcast. Every lane of a segment ends up with
+// the identical value; fixed order -> deterministic. Only entries [lo, hi) are summed (compile-time pruned).
 template <class T, int NV>
-__device__ __forceinline__ void seg_sum(T (&v)[NV], const int s0, const int n, const int nmax) {
-  T acc[NV];
+__device__ __forceinline__ void seg_sum(T (&v)[NV], const int s0, const int n, const int nmax, const int i, const int lo = 0, const int hi = NV) {
+  constexpr unsigned FULL = 0xffffffffu;
+  for (int d = 1; d < nmax; d <<= 1) {
 #pragma unroll
-  for (int q = 0; q < NV; ++q) acc[q] = T(0);
-  for (int t = 0; t < nmax; ++t) {
-    const int src = (s0 + t) & 31;
-#pragma unroll
-    for (int q = 0; q < NV; ++q) { const T o = __shfl_sync(0xffffffffu, v[q], src); if (t < n) acc[q] += o; }
+    for (int q = 0; q < NV; ++q) {
+      if (q >= lo && q < hi) { const T o = __shfl_up_sync(FULL, v[q], d); if (i >= d) v[q] += o; }
+    }
   }
+  const int lastl = (s0 + n - 1) & 31;
 #pragma unroll
-  for (int q = 0; q < NV; ++q) v[q] = acc[q];
+  for (int q = 0; q < NV; ++q) if (q >= lo && q < hi) v[q] = __shfl_sync(FULL, v[q], lastl);
 }
 template <class T> __device__ __forceinline__ void cswap(T& a, T& b, bool sw) { const T t = a; a = sw ? b : a; b = sw ? t : b; }
 
@@ -401,7 +404,7 @@ __device__ __forceinline__ void seg_householder(T (&x)[2][3], const T e0, const 
     T nn[3] = {T(0), T(0), T(0)};
 #pragma unroll
     for (int c = 0; c < 3; ++c) if (c >= k) nn[c] = (ge0 ? x[0][c] * x[0][c] : T(0)) + (ge1 ? x[1][c] * x[1][c] : T(0));
-    seg_sum<T, 3>(nn, s0, n, nmax);
+    seg_sum<T, 3>(nn, s0, n, nmax, i, k);
 #pragma unroll
     for (int c = 0; c < 3; ++c) if (c >= k) nn[c] += L[0][c] * L[0][c] + L[1][c] * L[1][c] + L[2][c] * L[2][c];
     int best = k;
@@ -419,7 +422,7 @@ __device__ __forceinline__ void seg_householder(T (&x)[2][3], const T e0, const 
     }
     const T c0 = __shfl_sync(FULL, (k & 1) ? x[1][k] : x[0][k], own);
     T t2[1] = {(gt0 ? x[0][k] * x[0][k] : T(0)) + (gt1 ? x[1][k] * x[1][k] : T(0))};
-    seg_sum<T, 1>(t2, s0, n, nmax);
+    seg_sum<T, 1>(t2, s0, n, nmax, i);
     const T tail2 = t2[0] + L[0][k] * L[0][k] + L[1][k] * L[1][k] + L[2][k] * L[2][k];
     const bool degenerate = tail2 <= tiny;
     T beta = tsqrt(c0 * c0 + tail2);
@@ -437,7 +440,7 @@ __device__ __forceinline__ void seg_householder(T (&x)[2][3], const T e0, const 
     T dots[2] = {T(0), T(0)};
 #pragma unroll
     for (int c = 0; c < 3; ++c) if (c > k) dots[c - k - 1] = (gt0 ? x[0][k] * x[0][c] : T(0)) + (gt1 ? x[1][k] * x[1][c] : T(0));
-    if (k < 2) seg_sum<T, 2>(dots, s0, n, nmax);
+    if (k < 2) seg_sum<T, 2>(dots, s0, n, nmax, i, 0, 2 - k);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       if (c > k) {
@@ -466,7 +469,7 @@ __device__ __forceinline__ void seg_householder(T (&x)[2][3], const T e0, const 
     T dots[2] = {T(0), T(0)};
 #pragma unroll
     for (int c = 0; c < 3; ++c) if (c > k) dots[c - k - 1] = (gt0 ? x[0][k] * x[0][c] : T(0)) + (gt1 ? x[1][k] * x[1][c] : T(0));
-    if (k < 2) seg_sum<T, 2>(dots, s0, n, nmax);
+    if (k < 2) seg_sum<T, 2>(dots, s0, n, nmax, i, 0, 2 - k);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       if (c > k) {
@@ -487,17 +490,17 @@ __device__ __forceinline__ void seg_householder(T (&x)[2][3], const T e0, const 
     if (lt1) x[1][k] = T(0);
   }
   cq[0] = x[0][0] * e0 + x[1][0] * e1; cq[1] = x[0][1] * e0 + x[1][1] * e1; cq[2] = x[0][2] * e0 + x[1][2] * e1;
-  seg_sum<T, 3>(cq, s0, n, nmax);
+  seg_sum<T, 3>(cq, s0, n, nmax, i);
 }
 
 // Normal-equation point factor (CHOLESKY variant; single-observation points): V = Jp^T Jp + lambda I = L D L^T,
 // R := D^{1/2} L^T, Q1 rows := Jp rows * R^{-1}.
 template <class T>
-__device__ __forceinline__ void seg_normal(T (&x)[2][3], const T e0, const T e1, const T lambda, const int s0, const int n, const int nmax,
+__device__ __forceinline__ void seg_normal(T (&x)[2][3], const T e0, const T e1, const T lambda, const int s0, const int n, const int i, const int nmax,
                                            T (&R)[6], int& pm, T (&cq)[3]) {
   T v[6] = {x[0][0] * x[0][0] + x[1][0] * x[1][0], x[0][1] * x[0][0] + x[1][1] * x[1][0], x[0][1] * x[0][1] + x[1][1] * x[1][1],
             x[0][2] * x[0][0] + x[1][2] * x[1][0], x[0][2] * x[0][1] + x[1][2] * x[1][1], x[0][2] * x[0][2] + x[1][2] * x[1][2]};
-  seg_sum<T, 6>(v, s0, n, nmax);
+  seg_sum<T, 6>(v, s0, n, nmax, i);
   const T v00 = v[0] + lambda, v10 = v[1], v11 = v[2] + lambda, v20 = v[3], v21 = v[4], v22 = v[5] + lambda;
   const T d0 = v00, l10 = v10 / d0, l20 = v20 / d0;
   const T d1 = v11 - l10 * l10 * d0, l21 = (v21 - l20 * l10 * d0) / d1;
@@ -514,7 +517,7 @@ __device__ __forceinline__ void seg_normal(T (&x)[2][3], const T e0, const T e1,
     x[a2][0] = y0; x[a2][1] = y1; x[a2][2] = y2;
   }
   cq[0] = x[0][0] * e0 + x[1][0] * e1; cq[1] = x[0][1] * e0 + x[1][1] * e1; cq[2] = x[0][2] * e0 + x[1][2] * e1;
-  seg_sum<T, 3>(cq, s0, n, nmax);
+  seg_sum<T, 3>(cq, s0, n, nmax, i);
 }
 
 template <class T>
@@ -544,14 +547,14 @@ __global__ void __launch_bounds__(TILE, 4) k_point_factor_warp(TileArgs<T> a, in
   }
   const int nmax = __reduce_max_sync(FULL, n);
   T G[3] = {x[0][0] * e0 + x[1][0] * e1, x[0][1] * e0 + x[1][1] * e1, x[0][2] * e0 + x[1][2] * e1};
-  seg_sum<T, 3>(G, s0, n, nmax);
+  seg_sum<T, 3>(G, s0, n, nmax, i);
   const bool use_h = (a.factor == PF_HOUSEHOLDER) && n >= 2;
   T R[6], cq[3]; int pm = 0;
   T xh[2][3], Rh[6], ch[3]; int pmh = 0;
 #pragma unroll
   for (int q = 0; q < 3; ++q) { xh[0][q] = x[0][q]; xh[1][q] = x[1][q]; }
   if (__any_sync(FULL, use_h)) seg_householder<T>(xh, e0, e1, tsqrt(a.lambda), s0, n, i, nmax, Rh, pmh, ch);
-  if (__any_sync(FULL, !use_h)) seg_normal<T>(x, e0, e1, a.lambda, s0, n, nmax, R, pm, cq);
+  if (__any_sync(FULL, !use_h)) seg_normal<T>(x, e0, e1, a.lambda, s0, n, i, nmax, R, pm, cq);
   if (use_h) {
 #pragma unroll
     for (int q = 0; q < 3; ++q) { x[0][q] = xh[0][q]; x[1][q] = xh[1][q]; cq[q] = ch[q]; }
