@@ -581,9 +581,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
 #endif
 #ifdef BA_DENSE_TICKS
   long long t2 = clock64();
+#define TICKT(th, i) { if (threadIdx.x == (th)) { const long long t1_ = clock64(); sm.tc[i] += t1_ - t2; t2 = t1_; } __syncwarp(); }
 #define TICKC(i) { if (threadIdx.x == 32) { const long long t1_ = clock64(); sm.tc[i] += t1_ - t2; t2 = t1_; } __syncwarp(); }
 #else
 #define TICKC(i) {}
+#define TICKT(th, i) {}
 #endif
   // per-thread constants of the tile-op path
   int aoff[NCP], soff[NCP];
@@ -664,6 +666,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
     const int ri = (warp < 4) ? warp - 1 : warp - 2;  // 0..5 over warps 1,2,3,5,6,7
     int it = row_warp ? k + 1 + rank + NC * ri : last + 1;
     bool pre = row_warp && (it <= last);
+    TICKT(0, 15) TICKT(32, 14)
     if (tid == 0) sm.pn.progress = 0;
     if (upd) {
       stage_tile_cta(sBop, k, kp0);
@@ -690,6 +693,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
     const T zr = *((tid < NB && k0 + tid < n) ? rhs + k0 + tid : zp);
     cp_async_wait_all();
     __syncthreads();
+    TICKT(0, 8)
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = team + 2 * u;
@@ -710,6 +714,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
     }
     if (tid < NB) sm.pn.sz[tid] = zr;
     __syncthreads();
+    TICKT(0, 9) TICKT(32, 14)
     T a[NB];
     auto fetch_issue = [&](const int t, bool& use_mma) {  // later passes only: start fetching row tile (t, k)
       use_mma = upd && (t <= k - 1 + bt);
@@ -753,6 +758,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
       const T d = sm.pn.sd[lane];
       sm.sdU[k & 1][lane] = d;
       if (rank == 0 && k0 + lane < n && (d == T(0) || !(d == d))) atomicCAS(info, 0, k0 + lane + 1);
+      TICKT(0, 10)
     } else if (pre) {
 #pragma unroll
       for (int c = 0; c < NB; ++c) a[c] = wbuf[lane][c];
@@ -794,7 +800,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
         T* out = do_w ? (Wbuf + (size_t)k * NB * NB + lane) : &wbuf[lane][0];
         const int ostride = do_w ? NB : 1;
         const T s = warp_trsm32<T>(a, sm.pn, out, ostride, !do_w, 0);
-        TICKC(12)
+        TICKT(32, 11)
         if (do_w) do_w = false;
         else {
           if (gi < n) rhs[gi] = rold - s;
@@ -819,9 +825,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
         }
       }
     }
-    TICKC(14)
+    TICKT(32, 12)
     __syncthreads();  // everyone is done with pn and the tile buffers before they are reused
-    TICKC(15)
+    TICKT(0, 13) TICKT(32, 14)
   };
 
   // ---- the remaining tiles (columns >= k+2) receive panel k's update in 2x2 blocks of tiles: block (I, J),
@@ -1048,9 +1054,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
   }
   TICK(5)
   if (dbg && rank == C - 1 && tid == 128) for (int i = 0; i < 8; ++i) dbg[i] = sm.tc[i];   // an update CTA
-  if (dbg && rank == 0 && tid == 32) for (int i = 8; i < 16; ++i) dbg[i] = sm.tc[i];         // a chain CTA's row warp
+  if (dbg && rank == 0 && tid == 0) for (int i = 8; i < 16; ++i) dbg[i] = sm.tc[i];          // chain CTA 0: warp 0 / warp 1 ticks
 #undef TICK
 #undef TICKC
+#undef TICKT
 }
 
 // ---- helpers of the two-sided factorisation (ba_gpu.cu): the bottom part of S is eliminated from the last row

@@ -8,7 +8,7 @@ for _ in range(3):
 s.set_profiling(True); s.compute(1e-12 * cn2); s.solve_try(); s.reject(); print("stage_ms", s.stage_ms())
 c = s.debug_counters()
 names = ["-", "upd CTA: loop top", "upd CTA: (chain skipped)", "upd CTA: block phase", "upd CTA: wait at cluster.sync", "backward(total)", "-", "-",
-         "w1: -", "w1: -", "w1: -", "w1: -", "w1: trsm (incl. waiting for the factor)", "w1: -", "w1: whole chain except trsm", "w1: end barrier + outside"]
+         "w0: stage + wait + barrier", "w0: column products + barrier", "w0: factor", "w1: trsm (after products barrier)", "w1: write-out", "w0: publish + wait for row warps", "w1: (other)", "w0: outside chain"]
 nt = (9 * p.N + 31) // 32
 for n, v in zip(names, c):
     print(f"{n:42s} {v:12d} cycles  = {v/1.9e3:9.1f} us total, {v/1.9e3/nt:6.2f} us/panel")
