@@ -696,7 +696,18 @@ struct Impl : ba_handle {
     CK(cudaGetLastError());
     QRMat<T> Q{G, ld, n, kd, ku};
     void* args[] = {&Q, &tauv, &rhs};
-    CK(cudaLaunchCooperativeKernel((void*)k_band_qr<T>, dim3(coop_grid_qr), dim3(QR_THREADS), args, 0, stream));
+    if (kd + QR_PB <= 32 * QR_MAXR) {  // banded case: reflectors in shared memory, columns in registers
+      const size_t smem = ((size_t)QR_PB * (kd + QR_PB) + QR_PB + QR_THREADS / 32 + 2) * sizeof(T);
+      CK(cudaFuncSetAttribute(k_band_qr_reg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 0, sms = 0;
+      CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_qr_reg<T>, QR_THREADS, smem));
+      const int want = (std::min(n - 1, 2 * kd) + 1 + QR_THREADS / 32 - 1) / (QR_THREADS / 32);  // one warp per trailing column
+      const int grid = std::max(1, std::min(std::max(occ, 1) * sms, want));
+      CK(cudaLaunchCooperativeKernel((void*)k_band_qr_reg<T>, dim3(grid), dim3(QR_THREADS), args, smem, stream));
+    } else {
+      CK(cudaLaunchCooperativeKernel((void*)k_band_qr<T>, dim3(coop_grid_qr), dim3(QR_THREADS), args, 0, stream));
+    }
     launches++;
     return BA_OK;
   }
@@ -897,7 +908,7 @@ struct Impl : ba_handle {
 extern "C" {
 
 const char* ba_last_error(void) { return g_err.c_str(); }
-const char* ba_version(void) { return "ba_b200 0.1 (sm_100a; kernels: k_schur, k_backsub_eval, k_band_ldlt, k_band_qr)"; }
+const char* ba_version(void) { return "ba_b200 0.2 (sm_100a; kernels: k_point_factor_warp, k_schur_diag/gather, k_band_ldlt_cluster, k_backsub_eval, k_band_qr)"; }
 
 int ba_create(ba_handle** out, int N, int M, int K, const int* view, const int* point, const double* meas,
               double inlier_threshold, int precision, int variant, int device) {

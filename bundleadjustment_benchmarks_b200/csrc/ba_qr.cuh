@@ -135,6 +135,122 @@ __global__ void __launch_bounds__(QR_THREADS) k_band_qr(QRMat<T> Q, T* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register/shared-memory variant for kd + QR_PB <= 32 * QR_MAXR rows per reflector (the banded case):
+// the panel is factored by CTA 0 entirely in shared memory; for the trailing update every CTA stages the
+// panel's reflector vectors in shared memory once and each warp keeps its column in REGISTERS while the
+// QR_PB reflectors are applied (one load and one store of the column per panel instead of one per
+// reflector, reflector vectors from shared memory instead of L2).
+// ---------------------------------------------------------------------------------------------
+constexpr int QR_MAXR = 20;  // rows per lane held in registers
+
+template <class T>
+__global__ void __launch_bounds__(QR_THREADS) k_band_qr_reg(QRMat<T> Q, T* __restrict__ tauv, T* __restrict__ rhs) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char qr_smem_raw[];
+  const int n = Q.n, kd = Q.kd, ku = Q.ku;
+  const int LV = kd + QR_PB;                       // rows k0 .. k0+LV-1 cover every reflector of a panel
+  T* sV = reinterpret_cast<T*>(qr_smem_raw);       // [QR_PB][LV]: panel columns (phase 1) / reflector vectors (phase 2)
+  T* stau = sV + QR_PB * LV;                       // [QR_PB]
+  T* sred = stau + QR_PB;                          // [QR_THREADS / 32 + 2]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = QR_THREADS / 32;
+  const int gwarp = blockIdx.x * nw + warp, nwarps = gridDim.x * nw;
+  for (int k0 = 0; k0 < n; k0 += QR_PB) {
+    const int pb = min(QR_PB, n - k0);
+    if (blockIdx.x == 0) {
+      // panel columns into shared memory: sV[c][r] = G(k0 + r, k0 + c), rows k0 .. min(n-1, k0+c+kd)
+      for (int idx = tid; idx < pb * LV; idx += QR_THREADS) {
+        const int c = idx / LV, r = idx - c * LV, i = k0 + r, j = k0 + c;
+        sV[idx] = (i < n && i <= j + kd) ? gq(Q, i, j) : T(0);
+      }
+      __syncthreads();
+      for (int c = 0; c < pb; ++c) {
+        T* v = sV + c * LV;
+        const int rend = min(n - 1, k0 + c + kd) - k0;  // last local row of this column
+        T s = T(0);
+        for (int r = c + 1 + tid; r <= rend; r += QR_THREADS) s += v[r] * v[r];
+        s = warp_sum(s);
+        if (lane == 0) sred[warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+          T tail2 = T(0);
+          for (int w = 0; w < nw; ++w) tail2 += sred[w];
+          const T c0 = v[c];
+          T tau = T(0), inv = T(0);
+          if (tail2 > (sizeof(T) == 8 ? T(2.2250738585072014e-308) : T(1.17549435e-38f))) {
+            T beta = sqrt(c0 * c0 + tail2);
+            if (c0 >= T(0)) beta = -beta;
+            inv = T(1) / (c0 - beta);
+            tau = (beta - c0) / beta;
+            v[c] = beta;
+          }
+          stau[c] = tau; sred[nw] = inv;
+        }
+        __syncthreads();
+        const T tau = stau[c], inv = sred[nw];
+        if (tau != T(0)) for (int r = c + 1 + tid; r <= rend; r += QR_THREADS) v[r] *= inv;
+        __syncthreads();
+        for (int cc = c + 1 + warp; cc < pb; cc += nw) {  // remaining panel columns: one warp each
+          if (tau == T(0)) continue;
+          T* x = sV + cc * LV;
+          T d = T(0);
+          for (int r = c + 1 + lane; r <= rend; r += 32) d += v[r] * x[r];
+          d = (warp_sum(d) + x[c]) * tau;
+          __syncwarp();
+          for (int r = c + 1 + lane; r <= rend; r += 32) x[r] -= d * v[r];
+          if (lane == 0) x[c] -= d;
+          __syncwarp();
+        }
+        __syncthreads();
+      }
+      for (int idx = tid; idx < pb * LV; idx += QR_THREADS) {
+        const int c = idx / LV, r = idx - c * LV, i = k0 + r, j = k0 + c;
+        if (i < n && i <= j + kd) gq(Q, i, j) = sV[idx];
+      }
+      if (tid < pb) tauv[k0 + tid] = stau[tid];
+    }
+    grid.sync();
+    // reflector vectors of this panel -> shared memory (v(col) = 1 implicit; sV[c][r] valid for r > c)
+    for (int idx = tid; idx < pb * LV; idx += QR_THREADS) {
+      const int c = idx / LV, r = idx - c * LV, i = k0 + r, j = k0 + c;
+      sV[idx] = (r > c && i < n && i <= j + kd) ? gq(Q, i, j) : T(0);
+    }
+    if (tid < pb) stau[tid] = tauv[k0 + tid];
+    __syncthreads();
+    const int jlast = min(n - 1, k0 + pb - 1 + ku);
+    const int ntrail = jlast - (k0 + pb) + 1;  // may be <= 0
+    const int rlast = min(n - 1, k0 + pb - 1 + kd);  // last row any reflector of the panel touches
+    for (int w = gwarp; w < ntrail + 1; w += nwarps) {
+      const int j = (w == ntrail) ? n : (k0 + pb + w);
+      T* xp = (w == ntrail) ? rhs : (Q.G + (size_t)j * Q.ld + (ku - j));  // x(r) = xp[r]
+      const int rlo = (w == ntrail) ? k0 : max(k0, j - ku);  // rows above j - ku are not part of column j's band
+      T x[QR_MAXR];
+#pragma unroll
+      for (int t = 0; t < QR_MAXR; ++t) { const int i = k0 + lane + 32 * t; x[t] = (i >= rlo && i <= rlast) ? xp[i] : T(0); }
+      for (int c = 0; c < pb; ++c) {
+        const int col = k0 + c;
+        const T tau = stau[c];
+        if ((w != ntrail && j > col + ku) || tau == T(0)) continue;
+        const T* v = sV + c * LV;
+        T d = T(0);
+#pragma unroll
+        for (int t = 0; t < QR_MAXR; ++t) { const int r = lane + 32 * t; if (r < LV) d += v[r] * x[t]; }  // v[r] = 0 for r <= c and beyond the column
+        d = warp_sum(d);
+        // x(col): row local index c (< QR_PB <= 32) lives in lane c, register 0
+        const T xcol = __shfl_sync(0xffffffffu, x[0], c);
+        d = (d + xcol) * tau;
+#pragma unroll
+        for (int t = 0; t < QR_MAXR; ++t) { const int r = lane + 32 * t; if (r < LV) x[t] -= d * v[r]; }
+        if (lane == c) x[0] -= d;
+      }
+#pragma unroll
+      for (int t = 0; t < QR_MAXR; ++t) { const int i = k0 + lane + 32 * t; if (i >= rlo && i <= rlast) xp[i] = x[t]; }
+    }
+    grid.sync();
+  }
+}
+
 // y = sign * R^-1 (Q^T g): blocked upper-triangular back substitution, single CTA.
 template <class T>
 __global__ void __launch_bounds__(QR_SOLVE_THREADS) k_band_qr_backsolve(QRMat<T> Q, T* __restrict__ rhs, T* __restrict__ y, T sign) {
