@@ -68,12 +68,6 @@ NcclApi g_nccl;
 // ------------------------------------------------------------------------------- small kernels
 using namespace ba;
 
-template <class T>
-__global__ void k_add_diag(T* __restrict__ Sv, size_t lds, int n, T diag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) Sv[(size_t)i * lds + i] += diag;
-}
-
 // mode 0: energy partials; 1: + residuals out; 2: Jacobian blocks out; 3: column-norm accumulation
 template <class T, int MODE>
 __global__ void __launch_bounds__(256) k_obs(int K, const int* __restrict__ view, const int* __restrict__ point, const T* __restrict__ meas,
@@ -170,16 +164,6 @@ __global__ void __launch_bounds__(1024) k_cam_update(int N, const T* __restrict_
   if (threadIdx.x == 0) { out_norm2[0] = s[0]; out_dot[0] = s2[0]; }
 }
 
-template <class T> __global__ void k_neg_copy(const T* __restrict__ a, T* __restrict__ b, int n, T sign) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) b[i] = sign * a[i];
-}
-
-template <class A, class B> __global__ void k_convert(const A* __restrict__ a, B* __restrict__ b, size_t n) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) b[i] = (B)a[i];
-}
-
 template <class T> struct DevBuf {
   T* p = nullptr; size_t n = 0;
   cudaError_t alloc(size_t count) { free(); n = count; return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)); }
@@ -237,7 +221,7 @@ struct Impl : ba_handle {
   int nunits = 0, nbig = 0;
   DevBuf<T> d_P, d_Q, d_Pt;  // per-observation / per-point records written by k_point_factor
   int nblocks = 0, gather_grid = 0;
-  DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g */, d_keep, d_y, d_dvec, d_tmp;
+  DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g | gJ */, d_keep, d_dvec, d_tmp;
   DevBuf<T> d_qr;  // general band copy for the Householder QR of S
   DevBuf<T> d_W;   // L_kk^-1 tiles kept by the cluster LDLT for the backward pass
   DevBuf<T> d_rev, d_dvec2, d_W2, d_y2, d_WM;  // two-sided factorisation: reversed bottom system [S' | g'], its D, W, y; middle W
@@ -280,7 +264,7 @@ struct Impl : ba_handle {
     ldsv = pad_lds(kd);
     red_count = (size_t)n * (ldsv + 1);
     CK(d_red.alloc(red_count + 2 * (size_t)n));
-    CK(d_y.alloc(n)); CK(d_dvec.alloc((size_t)n + NB));  // D is read/written in whole 32-wide panels
+    CK(d_dvec.alloc((size_t)n + NB));  // D is read/written in whole 32-wide panels
     if (keep_reduced) CK(d_keep.alloc(red_count + n));
     d_qr.free();
     return BA_OK;

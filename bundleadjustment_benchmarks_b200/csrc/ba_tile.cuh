@@ -37,11 +37,8 @@ template <class T> struct TileSmem {
   int perm[TP];    // per point: packed column permutation
   int ptObs0[TP];  // per point: first local observation
   int ptN[TP];     // per point: observation count
-  int pairOff[TP + 1];
   double red[3 * (TILE / 32)];
 };
-
-template <class T> __device__ __forceinline__ void atomic_add(T* p, T v) { atomicAdd(p, v); }
 
 // ---------------------------------------------------------------------------------------------
 // Phase 2: one lane per point. Rows rho = 2*i + a live in sm.Q[(3a+b)*TP + lo + i]; the three

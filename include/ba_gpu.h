@@ -100,18 +100,19 @@ int ba_get_jacobian(ba_handle* h, double* Jc, double* Jp);
 
 /* Counters: kernels launched by this handle since creation; device milliseconds of the last
  * ba_compute / ba_solve_try by stage (CUDA events on the handle's stream).
- * stage_ms[8]: 0 zero/init S, 1 schur kernel, 2 all-reduce, 3 factor, 4 reduced solve,
- * 5 camera update, 6 back-substitution + test energy, 7 reductions. */
+ * stage_ms[8]: 0 per-point factor (Jacobian + point QR + records), 1 reduced-system gather (diagonal +
+ * off-diagonal blocks), 2 all-reduce, 3 factor, 4 reduced solve, 5 camera update,
+ * 6 back-substitution + test energy, 7 reductions. */
 int ba_launch_count(ba_handle* h, long long* launches);
 int ba_stage_ms(ba_handle* h, double* stage_ms8);
 int ba_set_profiling(ba_handle* h, int enable);
-/* Whole-region device timing with CUDA events recorded on the handle's own stream (the stream every
- * kernel of this handle is launched on): start, run any number of calls, stop -> elapsed ms. */
 /* Debug: 16 device cycle counters of the last dense-stage kernel (phase split; see csrc/ba_dense.cuh). */
 int ba_debug_counters(ba_handle* h, long long* out16);
 /* Test hook (not on the hot path): factor + solve S y = g for an arbitrary symmetric band matrix (S dense
  * row-major n x n, half-bandwidth kd) with this handle's reduced-camera-block solver (LDL^T or QR by variant). */
 int ba_debug_band_solve(ba_handle* h, int n, int kd, const double* S, const double* g, double* y);
+/* Whole-region device timing with CUDA events recorded on the handle's own stream (the stream every
+ * kernel of this handle is launched on): start, run any number of calls, stop -> elapsed ms. */
 int ba_timer_start(ba_handle* h);
 int ba_timer_stop(ba_handle* h, double* elapsed_ms);
 
