@@ -283,12 +283,12 @@ def run_ours(args):
     bw = s.bandwidth
     kd = min(9 * N - 1, 9 * bw + 8)
     band_bytes = 9 * N * (kd + 1) * sz
-    pairs = int(sum(n * (n + 1) // 2 for n in np.bincount(prob.point, minlength=M)))
-    rec = 36 * sz  # bytes of one per-observation record (csrc/ba_tile.cuh)
+    pairs = int(sum(n * (n - 1) // 2 for n in np.bincount(prob.point, minlength=M)))  # off-diagonal pair list entries
+    rec = 28 * sz  # bytes of one per-observation record, P or D (csrc/ba_tile.cuh)
     alg_bytes = {
-        # observations in (indices, measurement), points + cameras in, P and Q records + point records out
+        # observations in (indices, measurement), points + cameras in, P and D records + point records out
         "k_point_factor": K * (12 + 2 * sz) + 3 * M * sz + 16 * N * sz + 2 * K * rec + 16 * M * sz,
-        # every P record once for the pair sums (re-reads are served by L2), every Q record once for the
+        # every P record once for the pair sums (re-reads are served by L2), every D record once for the
         # diagonal blocks, the pair list, S band + g + gJ out
         "k_schur_gather": 2 * K * rec + 8 * pairs + band_bytes + 2 * 9 * N * sz,
         "k_backsub_eval": K * (12 + 2 * sz) + K * rec + 16 * M * sz + 9 * M * sz + 2 * 16 * N * sz + 9 * N * sz,

@@ -215,11 +215,11 @@ struct Impl : ba_handle {
   cudaEvent_t ev[9];
   cudaEvent_t tev[2] = {nullptr, nullptr};
   DevBuf<int> d_view, d_point, d_pt_start, d_tile_pt, d_info;
-  DevBuf<int> d_slot, d_cam_start, d_blk_a, d_blk_b, d_blk_start, d_blk_order, d_counter;  // static structure of the deterministic Schur gather
+  DevBuf<int> d_slot, d_cam_start, d_blk_a, d_blk_b, d_blk_start, d_counter;  // static structure of the deterministic Schur gather
   DevBuf<int2> d_pairs;
   DevBuf<int> d_unit_pt, d_big_pt;  // warp units (points with <= 32 observations) / tiles of the larger points
   int nunits = 0, nbig = 0;
-  DevBuf<T> d_P, d_Q, d_Pt;  // per-observation / per-point records written by k_point_factor
+  DevBuf<T> d_P, d_D, d_Pt;  // per-observation (P, D) / per-point records written by k_point_factor*
   int nblocks = 0, gather_grid = 0;
   DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g | gJ */, d_keep, d_dvec, d_tmp;
   DevBuf<T> d_qr;  // general band copy for the Householder QR of S
@@ -350,8 +350,6 @@ struct Impl : ba_handle {
     // blocks are handed out in (a, b) order: concurrently processed blocks share cameras, so the P records of the
     // ~bw cameras in flight stay in L2 (largest-first order balanced slightly better but read 8 GB from HBM
     // instead of the 1.4 GB of records: profiles/r01_ncu_tiles_v2_summary.csv)
-    std::vector<int> blk_order(nblocks);
-    for (int b2 = 0; b2 < nblocks; ++b2) blk_order[b2] = b2;
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BA_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
@@ -374,10 +372,9 @@ struct Impl : ba_handle {
     if (nunits) CK(cudaMemcpyAsync(d_unit_pt.p, unit_pt.data(), unit_pt.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     if (nbig) CK(cudaMemcpyAsync(d_big_pt.p, big_pt.data(), big_pt.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(d_slot.alloc(K)); CK(d_cam_start.alloc(N + 1)); CK(d_blk_a.alloc(nblocks)); CK(d_blk_b.alloc(nblocks)); CK(d_blk_start.alloc(nblocks + 1));
-    CK(d_blk_order.alloc(nblocks)); CK(d_counter.alloc(1));
-    CK(cudaMemcpyAsync(d_blk_order.p, blk_order.data(), nblocks * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(d_counter.alloc(1));
     CK(d_pairs.alloc(pairs.size()));
-    CK(d_P.alloc((size_t)K * REC)); CK(d_Q.alloc((size_t)K * REC)); CK(d_Pt.alloc((size_t)M * PREC));
+    CK(d_P.alloc((size_t)K * REC)); CK(d_D.alloc((size_t)K * REC)); CK(d_Pt.alloc((size_t)M * PREC));
     CK(cudaMemcpyAsync(d_slot.p, slot.data(), K * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_cam_start.p, cam_start.data(), (N + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_blk_a.p, blk_a.data(), nblocks * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -395,7 +392,10 @@ struct Impl : ba_handle {
     CK(cudaFuncSetAttribute(k_point_factor<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<T>)));
     int occ = 0, sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_schur_gather<T>, GATHER_THREADS, 0));
+    CK(cudaFuncSetAttribute(k_schur_gather<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gather_smem_bytes<T>()));
+    CK(cudaFuncSetAttribute(k_schur_diag<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem_bytes<T>()));
+    CK(cudaFuncSetAttribute(k_backsub_eval<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)backsub_smem_bytes<T>()));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_schur_gather<T>, GATHER_THREADS, gather_smem_bytes<T>()));
     gather_grid = std::max(1, std::min(std::max(occ, 1) * sms, (nblocks + GATHER_THREADS / 32 - 1) / (GATHER_THREADS / 32)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_ldlt<T>, DENSE_THREADS, 0));
     coop_grid = std::max(1, std::min(occ, 2)) * sms;
@@ -560,17 +560,17 @@ struct Impl : ba_handle {
     const T diag = (variant == BA_CHOLESKY) ? lamT : sl * sl;  // QR variants square the sqrt(lambda) rows
     mark(0);
     CK(cudaMemsetAsync(d_red.p, 0, (red_count + 2 * (size_t)n) * sizeof(T), stream));
-    if (nunits) { k_point_factor_warp<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, 0, stream>>>(tile_args(lamT), nunits, d_unit_pt.p, d_slot.p, d_P.p, d_Q.p, d_Pt.p); launches++; }
+    if (nunits) { k_point_factor_warp<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, 0, stream>>>(tile_args(lamT), nunits, d_unit_pt.p, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++; }
     if (nbig) {
       TileArgs<T> ab = tile_args(lamT); ab.tile_pt = d_big_pt.p;
-      k_point_factor<T><<<nbig, TILE, sizeof(TileSmem<T>), stream>>>(ab, 2, d_slot.p, d_P.p, d_Q.p, d_Pt.p); launches++;
+      k_point_factor<T><<<nbig, TILE, sizeof(TileSmem<T>), stream>>>(ab, 2, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++;
     }
     CK(cudaGetLastError());
     mark(1);
     CK(cudaMemsetAsync(d_counter.p, 0, sizeof(int), stream));
-    k_schur_diag<T><<<N, GATHER_THREADS, 0, stream>>>(d_cam_start.p, d_P.p, d_Q.p, Sv(), lds(), gvec(), gJvec(), rank == 0 ? diag : T(0));
+    k_schur_diag<T><<<N, DIAG_THREADS, diag_smem_bytes<T>(), stream>>>(d_cam_start.p, d_D.p, Sv(), lds(), gvec(), gJvec(), rank == 0 ? diag : T(0));
     if (nblocks > 0)
-      k_schur_gather<T><<<gather_grid, GATHER_THREADS, 0, stream>>>(nblocks, d_blk_order.p, d_blk_a.p, d_blk_b.p, d_blk_start.p, d_pairs.p, d_P.p,
+      k_schur_gather<T><<<gather_grid, GATHER_THREADS, gather_smem_bytes<T>(), stream>>>(nblocks, d_blk_a.p, d_blk_b.p, d_blk_start.p, d_pairs.p, d_P.p,
                                                                      Sv(), lds(), d_counter.p);
     launches += 2;
     CK(cudaGetLastError());
@@ -726,7 +726,7 @@ struct Impl : ba_handle {
     k_cam_update<T><<<1, 1024, 0, stream>>>(N, d_cams.p, d_dx_cam.p, gJvec(), d_cams_test.p, d_scal.p + 4, d_scal.p + 6);
     launches++;
     mark(6);
-    k_backsub_eval<T><<<ntiles, TILE, 0, stream>>>(tile_args(lamT), d_slot.p, d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
+    k_backsub_eval<T><<<ntiles, TILE, backsub_smem_bytes<T>(), stream>>>(tile_args(lamT), d_slot.p, d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
                                                     d_partials.p, ntiles);
     launches++;
     CK(cudaGetLastError());

@@ -278,20 +278,27 @@ __device__ __forceinline__ void tile_phases_123(const TileArgs<T>& a, TileSmem<T
 // synthetic scale) and make S differ from run to run. The structure of S is static (which point
 // contributes to which 9x9 camera-pair block), so it is built once on the host: every non-empty block
 // (a, b), b <= a, owns the list of (observation of a, observation of b) pairs of the points seen by both.
-// Pass 1 (k_point_factor, one CTA per point tile) stores per observation, at the observation's
-// CAMERA-MAJOR slot (observations sorted by (camera, point)),
-//   P record (36 scalars): R12_i = Q1_i^T Jc_i as [k][g][4] = {R12[k][3g..3g+2], 0}
-//   Q record (36 scalars): Jc_i as [r][g][4] = {Jc[r][3g..3g+2], e_r}, then [g][4] = {gobs[3g..3g+2], 0},
-//                          gobs = Jc^T e - R12^T c
+// Pass 1 (k_point_factor_warp / k_point_factor) stores per observation, at the observation's CAMERA-MAJOR
+// slot (observations sorted by (camera, point)), two records of REC = 28 scalars (224 / 112 bytes):
+//   P record: R12_i = Q1_i^T Jc_i, 3x9 row-major, one pad scalar              (off-diagonal blocks, back-substitution)
+//   D record: Jc_i 2x9 row-major | M_i = I2 - Q1_i Q1_i^T as m00 m01 m11 | w_i = e_i - Q1_i c | e_i | 3 pad
+//             (diagonal blocks: Jc^T Jc - R12^T R12 = Jc^T M Jc; g: Jc^T e - R12^T c = Jc^T w; gJ = Jc^T e)
 // and per point (R (6), c (3), G = Jp^T e (3), perm, pad) = 16 scalars.
-// Pass 2 (k_schur_gather, one warp per block) sums -R12_a^T R12_b over the block's pair list with 3x3
-// register tiles (9 lanes per pair, three pairs in flight per warp, fixed order), adds Jc^T Jc, g and
-// gJ = sum Jc^T e on the diagonal blocks and WRITES the block: every entry of S has exactly one writer,
-// so the result is bit-reproducible. Camera-major slots keep the working set of consecutive blocks (the
-// records of ~bw cameras) in L2. The back-substitution re-reads the P and point records instead of
-// re-evaluating the Jacobian and the point QR.
+// Pass 2: k_schur_gather (one warp per off-diagonal block, one LANE per pair with the whole 9x9 block in
+// registers, records staged through shared memory with cp.async one batch of 32 pairs ahead) and
+// k_schur_diag (one CTA per camera streaming the camera's contiguous D records, one lane per record)
+// WRITE the blocks: every entry of S has exactly one writer and a fixed summation order, so the result is
+// bit-reproducible. Camera-major slots keep the working set of consecutive blocks (the records of ~bw
+// cameras) in L2. The back-substitution re-reads the P and point records instead of re-evaluating the
+// Jacobian and the point QR.
+//
+// Why one lane per pair: the LSU delivers 128 bytes per clock per SM to the register file, and every
+// distinct 128-byte line touched by a warp instruction costs one pass. With 3x3 register tiles (9 lanes per
+// pair, r1 v3) each lane re-loads 6 operands per 9 FMAs from three different records per instruction: ncu
+// showed l1tex at 96 % and 25 passes per pair. A lane that owns the whole block needs 18 operands per 81
+// FMAs, and the staged records are read conflict-free (stride 30 doubles / 36 floats, 16-byte loads).
 // =============================================================================================
-constexpr int REC = 36;   // scalars per observation record
+constexpr int REC = 28;   // scalars per observation record (P and D)
 constexpr int PREC = 16;  // scalars per point record
 
 __device__ __forceinline__ void store4(double* p, double a, double b, double c, double d) {
@@ -307,10 +314,25 @@ __device__ __forceinline__ void load4(const float* p, float& a, float& b, float&
   const float4 u = __ldg(reinterpret_cast<const float4*>(p));
   a = u.x; b = u.y; c = u.z; d = u.w;
 }
+template <class T> __device__ __forceinline__ void store_rec(T* p, const T (&v)[REC]) {
+#pragma unroll
+  for (int c = 0; c < REC; c += 4) store4(p + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
+}
+// D record tail from the observation's thin-Q rows q[a][k], c = Q1^T e of its point and its residual
+template <class T>
+__device__ __forceinline__ void fill_drec_tail(T (&rec)[REC], const T q00, const T q01, const T q02, const T q10, const T q11, const T q12,
+                                               const T c0, const T c1, const T c2, const T e0, const T e1) {
+  rec[18] = T(1) - (q00 * q00 + q01 * q01 + q02 * q02);
+  rec[19] = -(q00 * q10 + q01 * q11 + q02 * q12);
+  rec[20] = T(1) - (q10 * q10 + q11 * q11 + q12 * q12);
+  rec[21] = e0 - (q00 * c0 + q01 * c1 + q02 * c2);
+  rec[22] = e1 - (q10 * c0 + q11 * c1 + q12 * c2);
+  rec[23] = e0; rec[24] = e1; rec[25] = T(0); rec[26] = T(0); rec[27] = T(0);
+}
 
 template <class T>
 __global__ void __launch_bounds__(TILE) k_point_factor(TileArgs<T> a, const int stride, const int* __restrict__ slot, T* __restrict__ Prec,
-                                                       T* __restrict__ Qrec, T* __restrict__ Ptrec) {
+                                                       T* __restrict__ Drec, T* __restrict__ Ptrec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<T>& sm = *reinterpret_cast<TileSmem<T>*>(smem_raw);
   const int t = threadIdx.x, tile = blockIdx.x;
@@ -321,31 +343,17 @@ __global__ void __launch_bounds__(TILE) k_point_factor(TileArgs<T> a, const int 
   __syncthreads();
   if (t < nobs) {
     const size_t sl = (size_t)__ldg(slot + o0 + t);
-    T* pr = Prec + sl * REC;
-    T* qr = Qrec + sl * REC;
     const T e0 = sm.E[t], e1 = sm.E[TP + t];
-    const T c0 = sm.C[lp], c1 = sm.C[TP + lp], c2 = sm.C[2 * TP + lp];
+    T rec[REC];
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
+    for (int b = 0; b < 27; ++b) rec[b] = sm.R12[b * TP + t];
+    rec[27] = T(0);
+    store_rec(Prec + sl * REC, rec);
 #pragma unroll
-      for (int g = 0; g < 3; ++g)
-        store4(pr + 12 * k + 4 * g, sm.R12[(9 * k + 3 * g) * TP + t], sm.R12[(9 * k + 3 * g + 1) * TP + t], sm.R12[(9 * k + 3 * g + 2) * TP + t], T(0));
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int g = 0; g < 3; ++g)
-        store4(qr + 12 * r + 4 * g, sm.Jc[(9 * r + 3 * g) * TP + t], sm.Jc[(9 * r + 3 * g + 1) * TP + t], sm.Jc[(9 * r + 3 * g + 2) * TP + t], r == 0 ? e0 : e1);
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      T v[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int b = 3 * g + i;
-        v[i] = sm.Jc[b * TP + t] * e0 + sm.Jc[(9 + b) * TP + t] * e1
-             - (sm.R12[b * TP + t] * c0 + sm.R12[(9 + b) * TP + t] * c1 + sm.R12[(18 + b) * TP + t] * c2);
-      }
-      store4(qr + 24 + 4 * g, v[0], v[1], v[2], T(0));
-    }
+    for (int b = 0; b < 18; ++b) rec[b] = sm.Jc[b * TP + t];
+    fill_drec_tail<T>(rec, sm.Q[0 * TP + t], sm.Q[1 * TP + t], sm.Q[2 * TP + t], sm.Q[3 * TP + t], sm.Q[4 * TP + t], sm.Q[5 * TP + t],
+                      sm.C[lp], sm.C[TP + lp], sm.C[2 * TP + lp], e0, e1);
+    store_rec(Drec + sl * REC, rec);
   }
   if (t < npts) {
     T* q = Ptrec + (size_t)(p0 + t) * PREC;
@@ -519,7 +527,7 @@ __device__ __forceinline__ void seg_normal(T (&x)[2][3], const T e0, const T e1,
 
 template <class T>
 __global__ void __launch_bounds__(TILE, 4) k_point_factor_warp(TileArgs<T> a, int nunits, const int* __restrict__ unit_pt, const int* __restrict__ slot,
-                                                            T* __restrict__ Prec, T* __restrict__ Qrec, T* __restrict__ Ptrec) {
+                                                            T* __restrict__ Prec, T* __restrict__ Drec, T* __restrict__ Ptrec) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, u = blockIdx.x * (TILE / 32) + (threadIdx.x >> 5);
   if (u >= nunits) return;
@@ -561,26 +569,17 @@ __global__ void __launch_bounds__(TILE, 4) k_point_factor_warp(TileArgs<T> a, in
   }
   if (!act) return;
   const size_t sl = (size_t)__ldg(slot + o);
-  T* pr = Prec + sl * REC;
-  T* qr = Qrec + sl * REC;
-  T gob[9];
-#pragma unroll
-  for (int b = 0; b < 9; ++b) gob[b] = jc[b] * e0 + jc[9 + b] * e1;
+  T rec[REC];
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      T r12[3];
+    for (int b = 0; b < 9; ++b) rec[9 * k + b] = x[0][k] * jc[b] + x[1][k] * jc[9 + b];
+  rec[27] = T(0);
+  store_rec(Prec + sl * REC, rec);
 #pragma unroll
-      for (int q = 0; q < 3; ++q) { const int b = 3 * g + q; r12[q] = x[0][k] * jc[b] + x[1][k] * jc[9 + b]; gob[b] -= r12[q] * cq[k]; }
-      store4(pr + 12 * k + 4 * g, r12[0], r12[1], r12[2], T(0));
-    }
-#pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int g = 0; g < 3; ++g) store4(qr + 12 * r + 4 * g, jc[9 * r + 3 * g], jc[9 * r + 3 * g + 1], jc[9 * r + 3 * g + 2], r == 0 ? e0 : e1);
-#pragma unroll
-  for (int g = 0; g < 3; ++g) store4(qr + 24 + 4 * g, gob[3 * g], gob[3 * g + 1], gob[3 * g + 2], T(0));
+  for (int b = 0; b < 18; ++b) rec[b] = jc[b];
+  fill_drec_tail<T>(rec, x[0][0], x[0][1], x[0][2], x[1][0], x[1][1], x[1][2], cq[0], cq[1], cq[2], e0, e1);
+  store_rec(Drec + sl * REC, rec);
   if (i == 0) {
     T* q = Ptrec + (size_t)pj * PREC;
     store4(q, R[0], R[1], R[2], R[3]);
@@ -590,169 +589,260 @@ __global__ void __launch_bounds__(TILE, 4) k_point_factor_warp(TileArgs<T> a, in
   }
 }
 
-// Off-diagonal blocks: one warp per block (a, b), b < a, blocks handed out largest-first through a global
-// counter (the result does not depend on which warp computes a block). Lanes 0..26: group = lane / 9 takes
-// every third pair, (P, Q) = 3x3 tile of the 9x9 block; lanes 27..31 idle. Two pairs per group are in
-// flight and the pair indices are fetched one batch ahead, so one memory latency is exposed per two pairs.
-constexpr int GATHER_THREADS = 256;
-template <class T>
-__global__ void __launch_bounds__(GATHER_THREADS, 2) k_schur_gather(int nblocks, const int* __restrict__ blk_order, const int* __restrict__ blk_a,
-                                                                    const int* __restrict__ blk_b, const int* __restrict__ blk_start,
-                                                                    const int2* __restrict__ pairs, const T* __restrict__ Prec,
-                                                                    T* __restrict__ Sv, size_t lds, int* __restrict__ counter) {
-  constexpr unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int grp = lane / 9, li = lane - 9 * grp, P = li / 3, Q = li - 3 * P;
-  const bool act = grp < 3;
-  while (true) {
-    int bi = 0;
-    if (lane == 0) bi = atomicAdd(counter, 1);
-    bi = __shfl_sync(FULL, bi, 0);
-    if (bi >= nblocks) break;
-    const int B = __ldg(blk_order + bi);
-    const int ca = __ldg(blk_a + B), cb = __ldg(blk_b + B);
-    const int s0 = __ldg(blk_start + B), s1 = __ldg(blk_start + B + 1);
-    T acc[3][3] = {{T(0), T(0), T(0)}, {T(0), T(0), T(0)}, {T(0), T(0), T(0)}};
-    if (act) {
-      int t = s0 + grp;
-      int2 n0 = make_int2(0, 0), n1 = make_int2(0, 0);
-      if (t < s1) n0 = __ldg(pairs + t);
-      if (t + 3 < s1) n1 = __ldg(pairs + t + 3);
-      while (t < s1) {
-        const int2 c0 = n0, c1 = n1;
-        const bool two = t + 3 < s1;
-        t += 6;
-        if (t < s1) n0 = __ldg(pairs + t);
-        if (t + 3 < s1) n1 = __ldg(pairs + t + 3);
-        const T* pa0 = Prec + (size_t)c0.x * REC + 4 * P;
-        const T* pb0 = Prec + (size_t)c0.y * REC + 4 * Q;
-        const T* pa1 = Prec + (size_t)(two ? c1.x : c0.x) * REC + 4 * P;
-        const T* pb1 = Prec + (size_t)(two ? c1.y : c0.y) * REC + 4 * Q;
-        T a0[3][4], b0[3][4], a1[3][4], b1[3][4];
+// ---------------------------------------------------------------------------------------------
+// Staging of records in shared memory. A record (REC scalars, 16-byte chunks) is copied with cp.async to a
+// shared-memory slot of SREC scalars: 8 consecutive lanes reading 16 bytes each at that stride hit 32
+// different banks (30 doubles = 60 words = 28 mod 32; 36 floats = 4 mod 32).
+// ---------------------------------------------------------------------------------------------
+template <class T> struct RecGeom {
+  static constexpr int EPC = 16 / (int)sizeof(T);      // scalars per 16-byte chunk
+  static constexpr int CPR = REC / EPC;                // chunks per record (14 / 7)
+  static constexpr int SREC = sizeof(T) == 8 ? 30 : 36;
+};
+__device__ __forceinline__ void rec_cp16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+template <class T> __device__ __forceinline__ void rec_cp1(T* smem_dst, const T* gsrc) {  // one scalar
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void rec_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void rec_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// scalars [lo, hi) of a staged record into registers, 16-byte shared loads (lo, hi multiples of EPC)
+template <int LO, int HI> __device__ __forceinline__ void lds_rec(const double* s, double (&r)[REC]) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          load4(pa0 + 12 * k, a0[k][0], a0[k][1], a0[k][2], a0[k][3]); load4(pb0 + 12 * k, b0[k][0], b0[k][1], b0[k][2], b0[k][3]);
-          load4(pa1 + 12 * k, a1[k][0], a1[k][1], a1[k][2], a1[k][3]); load4(pb1 + 12 * k, b1[k][0], b1[k][1], b1[k][2], b1[k][3]);
-        }
-        const T m1 = two ? T(1) : T(0);
+  for (int c = LO; c < HI; c += 2) { const double2 v = *reinterpret_cast<const double2*>(s + c); r[c] = v.x; r[c + 1] = v.y; }
+}
+template <int LO, int HI> __device__ __forceinline__ void lds_rec(const float* s, float (&r)[REC]) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const T x1 = a1[k][i] * m1;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) { acc[i][j] -= a0[k][i] * b0[k][j]; acc[i][j] -= x1 * b1[k][j]; }
-          }
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const T v1 = __shfl_down_sync(FULL, acc[i][j], 9), v2 = __shfl_down_sync(FULL, acc[i][j], 18);
-        acc[i][j] = (acc[i][j] + v1) + v2;
-      }
-    if (lane < 9) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Sv[(size_t)(9 * ca + 3 * P + i) * lds + 9 * cb + 3 * Q + j] = acc[i][j];
-    }
-  }
+  for (int c = LO; c < HI; c += 4) { const float4 v = *reinterpret_cast<const float4*>(s + c); r[c] = v.x; r[c + 1] = v.y; r[c + 2] = v.z; r[c + 3] = v.w; }
 }
 
-// Diagonal blocks: one CTA per camera streams the camera's (contiguous, camera-major) records:
-// S_aa = sum_i Jc_i^T Jc_i - R12_i^T R12_i (+ lambda I), g_a = sum_i gobs_i, gJ_a = sum_i Jc_i^T e_i.
-// 24 lane groups (8 warps x 3) stride over the records, two records per group in flight; per-warp shuffle
-// reduction, then a fixed-order sum over the 8 warps in shared memory (bit-reproducible).
+// ---------------------------------------------------------------------------------------------
+// Off-diagonal blocks S_ab = -sum_j R12_a^T R12_b: one warp per block (a, b), b < a, blocks handed out in
+// (a, b) order through a global counter (the result does not depend on which warp computes a block). The
+// block's pair list is cut into batches of 32 pairs; lane l owns pair l of the batch and accumulates its
+// 9x9 product in 81 registers. While batch i is being multiplied, the 64 records of batch i+1 (possibly the
+// first batch of the warp's next block) are in flight into the other half of the warp's staging buffer.
+// At the end of a block the 32 lane accumulators are summed in lane order through shared memory (fixed
+// order -> bit-reproducible) and lanes 0..26 write the block.
+// ---------------------------------------------------------------------------------------------
+constexpr int GATHER_WARPS = 6;
+constexpr int GATHER_THREADS = 32 * GATHER_WARPS;
+template <class T> constexpr size_t gather_smem_bytes() { return (size_t)GATHER_WARPS * 2 * 64 * RecGeom<T>::SREC * sizeof(T); }
+
 template <class T>
-__global__ void __launch_bounds__(GATHER_THREADS, 2) k_schur_diag(const int* __restrict__ cam_start, const T* __restrict__ Prec, const T* __restrict__ Qrec,
-                                                                  T* __restrict__ Sv, size_t lds, T* __restrict__ g, T* __restrict__ gJ, T lambda_diag) {
+__global__ void __launch_bounds__(GATHER_THREADS, 1) k_schur_gather(int nblocks, const int* __restrict__ blk_a, const int* __restrict__ blk_b,
+                                                                    const int* __restrict__ blk_start, const int2* __restrict__ pairs,
+                                                                    const T* __restrict__ Prec, T* __restrict__ Sv, size_t lds, int* __restrict__ counter) {
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int NW = GATHER_THREADS / 32;
-  __shared__ T part[NW][9][15];  // per warp, per 3x3 tile lane: 9 block entries + 3 g + 3 gJ
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ca = blockIdx.x;
-  const int grp = lane / 9, li = lane - 9 * grp, P = li / 3, Q = li - 3 * P;
-  const bool act = grp < 3;
-  const int q0 = __ldg(cam_start + ca), q1 = __ldg(cam_start + ca + 1);
-  T acc[3][3] = {{T(0), T(0), T(0)}, {T(0), T(0), T(0)}, {T(0), T(0), T(0)}};
-  T gacc[3] = {T(0), T(0), T(0)}, jacc[3] = {T(0), T(0), T(0)};
-  if (act) {
-    for (int sidx = q0 + warp * 3 + grp; sidx < q1; sidx += 2 * 3 * NW) {
-      const bool two = sidx + 3 * NW < q1;
-      const size_t r0 = (size_t)sidx * REC, r1 = (size_t)(two ? sidx + 3 * NW : sidx) * REC;
-      T ap[2][3][4], aq[2][3][4], jp[2][2][4], jq[2][2][4], gv[2][4];
+  constexpr int EPC = RecGeom<T>::EPC, CPR = RecGeom<T>::CPR, SR = RecGeom<T>::SREC;
+  extern __shared__ __align__(16) unsigned char gather_smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* const wbuf = reinterpret_cast<T*>(gather_smem_raw) + (size_t)warp * 2 * 64 * SR;
+  // batch iterator (warp-uniform state)
+  int t = 0, tend = 0, blk = -1;
+  bool exhausted = false;
+  auto next = [&](int& b_blk, int& b_start, int& b_cnt, bool& b_last) -> bool {
+    if (exhausted) return false;
+    if (t >= tend) {
+      int bi = 0;
+      if (lane == 0) bi = atomicAdd(counter, 1);
+      bi = __shfl_sync(FULL, bi, 0);
+      if (bi >= nblocks) { exhausted = true; return false; }
+      blk = bi; t = __ldg(blk_start + bi); tend = __ldg(blk_start + bi + 1);
+    }
+    b_blk = blk; b_start = t; b_cnt = min(32, tend - t); t += b_cnt; b_last = (t >= tend);
+    return true;
+  };
+  // records of the batch -> buf: slots 0..31 the a-records of the pairs, slots 32..63 the b-records
+  auto issue = [&](const int start, const int cnt, T* buf) {
+    int2 pr = make_int2(0, 0);
+    if (lane < cnt) pr = __ldg(pairs + start + lane);
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const size_t r = u ? r1 : r0;
+    for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          load4(Prec + r + 12 * k + 4 * P, ap[u][k][0], ap[u][k][1], ap[u][k][2], ap[u][k][3]);
-          load4(Prec + r + 12 * k + 4 * Q, aq[u][k][0], aq[u][k][1], aq[u][k][2], aq[u][k][3]);
-        }
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          load4(Qrec + r + 12 * rr + 4 * P, jp[u][rr][0], jp[u][rr][1], jp[u][rr][2], jp[u][rr][3]);
-          load4(Qrec + r + 12 * rr + 4 * Q, jq[u][rr][0], jq[u][rr][1], jq[u][rr][2], jq[u][rr][3]);
-        }
-        load4(Qrec + r + 24 + 4 * P, gv[u][0], gv[u][1], gv[u][2], gv[u][3]);
+      for (int q = 0; q < CPR; ++q) {
+        const int idx = lane + 32 * q, rec = idx / CPR, part = idx - rec * CPR;
+        const int sl = __shfl_sync(FULL, h ? pr.y : pr.x, rec);
+        if (rec < cnt) rec_cp16(buf + (size_t)(32 * h + rec) * SR + part * EPC, Prec + (size_t)sl * REC + part * EPC);
       }
+    }
+  };
+  T acc[81];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const T m = (u == 0 || two) ? T(1) : T(0);
+  for (int e = 0; e < 81; ++e) acc[e] = T(0);
+  int c_blk = 0, c_start = 0, c_cnt = 0; bool c_last = false;
+  bool have = next(c_blk, c_start, c_cnt, c_last);
+  if (have) issue(c_start, c_cnt, wbuf);
+  rec_commit();
+  int cur = 0;
+  while (have) {
+    int n_blk = 0, n_start = 0, n_cnt = 0; bool n_last = false;
+    const bool have_n = next(n_blk, n_start, n_cnt, n_last);
+    if (have_n) issue(n_start, n_cnt, wbuf + (size_t)(cur ^ 1) * 64 * SR);
+    rec_commit();
+    rec_wait<1>();
+    __syncwarp();
+    T* const buf = wbuf + (size_t)cur * 64 * SR;
+    if (lane < c_cnt) {
+      const T* pa = buf + (size_t)lane * SR;
+      const T* pb = buf + (size_t)(32 + lane) * SR;
+      T ra[REC], rb[REC];
+      // row k of R12 sits at scalars 9k .. 9k+8: stream the 16-byte chunks in three groups so that only the
+      // operands of one row (plus the chunk straddling into the next) are live next to the 81 accumulators
+      constexpr int G1 = (9 + EPC - 1) / EPC * EPC, G2 = (18 + EPC - 1) / EPC * EPC;
+      lds_rec<0, G1>(pa, ra); lds_rec<0, G1>(pb, rb);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+      for (int i = 0; i < 9; ++i)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            T v = jp[u][0][i] * jq[u][0][j] + jp[u][1][i] * jq[u][1][j];
+        for (int j = 0; j < 9; ++j) acc[9 * i + j] += ra[i] * rb[j];
+      lds_rec<G1, G2>(pa, ra); lds_rec<G1, G2>(pb, rb);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) v -= ap[u][k][i] * aq[u][k][j];
-            acc[i][j] += m * v;
+      for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) acc[9 * i + j] += ra[9 + i] * rb[9 + j];
+      lds_rec<G2, REC>(pa, ra); lds_rec<G2, REC>(pb, rb);
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) acc[9 * i + j] += ra[18 + i] * rb[18 + j];
+    }
+    __syncwarp();
+    if (c_last) {
+      // fixed-order sum over the 32 lanes, 27 entries at a time, through the (consumed) staging buffer
+      const int ca = __ldg(blk_a + c_blk), cb = __ldg(blk_b + c_blk);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+        for (int v = 0; v < 27; ++v) buf[v * 33 + lane] = acc[27 * ch + v];
+        __syncwarp();
+        if (lane < 27) {
+          T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+#pragma unroll
+          for (int l = 0; l < 32; l += 4) {
+            s0 += buf[lane * 33 + l]; s1 += buf[lane * 33 + l + 1]; s2 += buf[lane * 33 + l + 2]; s3 += buf[lane * 33 + l + 3];
           }
-          gacc[i] += m * gv[u][i];
-          jacc[i] += m * (jp[u][0][i] * jp[u][0][3] + jp[u][1][i] * jp[u][1][3]);
+          const int e = 27 * ch + lane, i = e / 9, j = e - 9 * i;
+          Sv[(size_t)(9 * ca + i) * lds + 9 * cb + j] = -((s0 + s1) + (s2 + s3));
         }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int e = 0; e < 81; ++e) acc[e] = T(0);
+    }
+    c_blk = n_blk; c_start = n_start; c_cnt = n_cnt; c_last = n_last; have = have_n;
+    cur ^= 1;
+  }
+  rec_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Diagonal blocks: one CTA per camera streams the camera's contiguous (camera-major) D records through
+// shared memory (three cp.async stages of 32 records per warp) and every lane accumulates
+//   S_aa += Jc^T M Jc (lower triangle, 45 entries),  g_a += Jc^T w,  gJ_a += Jc^T e
+// for its record. Fixed-order reduction over lanes, then over warps (bit-reproducible).
+// ---------------------------------------------------------------------------------------------
+constexpr int DIAG_WARPS = 8;
+constexpr int DIAG_THREADS = 32 * DIAG_WARPS;
+constexpr int DIAG_STAGES = 3;
+template <class T> constexpr size_t diag_smem_bytes() { return (size_t)DIAG_WARPS * DIAG_STAGES * 32 * RecGeom<T>::SREC * sizeof(T); }
+
+template <class T>
+__global__ void __launch_bounds__(DIAG_THREADS, 1) k_schur_diag(const int* __restrict__ cam_start, const T* __restrict__ Drec, T* __restrict__ Sv,
+                                                                size_t lds, T* __restrict__ g, T* __restrict__ gJ, T lambda_diag) {
+  constexpr int EPC = RecGeom<T>::EPC, CPR = RecGeom<T>::CPR, SR = RecGeom<T>::SREC;
+  extern __shared__ __align__(16) unsigned char diag_smem_raw[];
+  __shared__ T part[DIAG_WARPS][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ca = blockIdx.x;
+  T* const wbuf = reinterpret_cast<T*>(diag_smem_raw) + (size_t)warp * DIAG_STAGES * 32 * SR;
+  const int q0 = __ldg(cam_start + ca), q1 = __ldg(cam_start + ca + 1);
+  const int nbatch = (q1 - q0 + 31) / 32;
+  auto issue = [&](const int bi, T* buf) {
+    if (bi < nbatch) {
+      const int base = q0 + 32 * bi, cnt = min(32, q1 - base);
+      const T* src = Drec + (size_t)base * REC;
+#pragma unroll
+      for (int q = 0; q < CPR; ++q) {
+        const int idx = lane + 32 * q, rec = idx / CPR, part_ = idx - rec * CPR;
+        if (rec < cnt) rec_cp16(buf + (size_t)rec * SR + part_ * EPC, src + (size_t)idx * EPC);
       }
     }
+    rec_commit();
+  };
+  T acc[45], ga[9], gj[9];
+#pragma unroll
+  for (int e = 0; e < 45; ++e) acc[e] = T(0);
+#pragma unroll
+  for (int b = 0; b < 9; ++b) { ga[b] = T(0); gj[b] = T(0); }
+  issue(warp, wbuf);
+  issue(warp + DIAG_WARPS, wbuf + 32 * SR);
+  int st = 0;
+  for (int bi = warp; bi < nbatch; bi += DIAG_WARPS) {
+    int st2 = st + 2; if (st2 >= DIAG_STAGES) st2 -= DIAG_STAGES;
+    issue(bi + 2 * DIAG_WARPS, wbuf + (size_t)st2 * 32 * SR);
+    rec_wait<2>();
+    __syncwarp();
+    const int cnt = min(32, q1 - (q0 + 32 * bi));
+    if (lane < cnt) {
+      T r[REC];
+      lds_rec<0, REC>(wbuf + ((size_t)st * 32 + lane) * SR, r);
+      const T m00 = r[18], m01 = r[19], m11 = r[20], w0 = r[21], w1 = r[22], e0 = r[23], e1 = r[24];
+      T t0[9], t1[9];
+#pragma unroll
+      for (int b = 0; b < 9; ++b) {
+        t0[b] = m00 * r[b] + m01 * r[9 + b];
+        t1[b] = m01 * r[b] + m11 * r[9 + b];
+        ga[b] += r[b] * w0 + r[9 + b] * w1;
+        gj[b] += r[b] * e0 + r[9 + b] * e1;
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+          if (j <= i) acc[i * (i + 1) / 2 + j] += r[i] * t0[j] + r[9 + i] * t1[j];
+    }
+    __syncwarp();
+    st = st + 1; if (st >= DIAG_STAGES) st = 0;
   }
+  rec_wait<0>();
   __syncwarp();
+  // lanes -> warp sums (21 values at a time through the warp's staging buffer), then warps in fixed order
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
+  for (int ch = 0; ch < 3; ++ch) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const T v1 = __shfl_down_sync(FULL, acc[i][j], 9), v2 = __shfl_down_sync(FULL, acc[i][j], 18);
-      acc[i][j] = (acc[i][j] + v1) + v2;
+    for (int v = 0; v < 21; ++v) {
+      const int e = 21 * ch + v;
+      wbuf[v * 33 + lane] = (e < 45) ? acc[e < 45 ? e : 0] : (e < 54 ? ga[(e >= 45 && e < 54) ? e - 45 : 0] : gj[e >= 54 ? e - 54 : 0]);
     }
-    const T u1 = __shfl_down_sync(FULL, gacc[i], 9), u2 = __shfl_down_sync(FULL, gacc[i], 18);
-    gacc[i] = (gacc[i] + u1) + u2;
-    const T w1 = __shfl_down_sync(FULL, jacc[i], 9), w2 = __shfl_down_sync(FULL, jacc[i], 18);
-    jacc[i] = (jacc[i] + w1) + w2;
-  }
-  if (lane < 9) {
+    __syncwarp();
+    if (lane < 21) {
+      T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) part[warp][lane][3 * i + j] = acc[i][j];
-      part[warp][lane][9 + i] = gacc[i];
-      part[warp][lane][12 + i] = jacc[i];
+      for (int l = 0; l < 32; l += 4) {
+        s0 += wbuf[lane * 33 + l]; s1 += wbuf[lane * 33 + l + 1]; s2 += wbuf[lane * 33 + l + 2]; s3 += wbuf[lane * 33 + l + 3];
+      }
+      part[warp][21 * ch + lane] = (s0 + s1) + (s2 + s3);
     }
+    __syncwarp();
   }
   __syncthreads();
-  if (warp == 0 && lane < 9) {
-    T tot[15];
+  const int e = threadIdx.x;
+  if (e < 63) {
+    T v = T(0);
 #pragma unroll
-    for (int e = 0; e < 15; ++e) { T v = T(0); for (int w = 0; w < NW; ++w) v += part[w][lane][e]; tot[e] = v; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int row = 9 * ca + 3 * P + i;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int col = 9 * ca + 3 * Q + j;
-        if (col < row) Sv[(size_t)row * lds + col] = tot[3 * i + j];
-        else if (col == row) Sv[(size_t)row * lds + col] = tot[3 * i + j] + lambda_diag;
-      }
-      if (Q == 0) { g[row] = tot[9 + i]; gJ[row] = tot[12 + i]; }
+    for (int w = 0; w < DIAG_WARPS; ++w) v += part[w][e];
+    if (e < 45) {
+      int i = 0;
+      while ((i + 1) * (i + 2) / 2 <= e) ++i;
+      const int j = e - i * (i + 1) / 2;
+      Sv[(size_t)(9 * ca + i) * lds + 9 * ca + j] = (i == j) ? v + lambda_diag : v;
+    } else if (e < 54) {
+      g[9 * ca + e - 45] = v;
+    } else {
+      gJ[9 * ca + e - 54] = v;
     }
   }
 }
@@ -763,36 +853,53 @@ __global__ void __launch_bounds__(GATHER_THREADS, 2) k_schur_diag(const int* __r
 //   e_test = residual(cams_test, X_test); partial sums per tile:
 //     part[0] = sum e_test^2, part[1] = |dx_pts|^2, part[2] = sum_points G . dx_j (G = Jp^T e), so that
 //     dx^T(lambda dx + JtRes) = lambda |dx|^2 - part[2] - dx_cam . gJ.
+// The tile's P records (scattered camera-major slots) and the dx_cam rows of its observations are staged
+// with coalesced cp.async (consecutive lanes copy consecutive chunks of a record); a lane reading its own
+// 224-byte record and 9 dx_cam scalars straight from global memory costs one LSU pass per lane per
+// instruction (r1 v4: 27 passes per observation, l1tex 93 %).
 // ---------------------------------------------------------------------------------------------
+template <class T> constexpr size_t backsub_smem_bytes() { return (size_t)TILE * (RecGeom<T>::SREC + 9) * sizeof(T); }
+
 template <class T>
 __global__ void __launch_bounds__(TILE) k_backsub_eval(TileArgs<T> a, const int* __restrict__ slot, const T* __restrict__ Prec,
                                                        const T* __restrict__ Ptrec, const T* __restrict__ dx_cam, const T* __restrict__ cams_test,
                                                        T* __restrict__ dx_pt, T* __restrict__ X_test, double* __restrict__ partials, int ntiles) {
+  constexpr int EPC = RecGeom<T>::EPC, CPR = RecGeom<T>::CPR, SR = RecGeom<T>::SREC;
+  extern __shared__ __align__(16) unsigned char backsub_smem_raw[];
+  T* const sP = reinterpret_cast<T*>(backsub_smem_raw);  // [TILE][SR]
+  T* const sD = sP + (size_t)TILE * SR;                  // [TILE][9]
   __shared__ T su[3][TP];
   __shared__ T sx[3][TP];
   __shared__ double red[3 * (TILE / 32)];
   const int t = threadIdx.x, tile = blockIdx.x;
   const int p0 = a.tile_pt[tile], p1 = a.tile_pt[tile + 1], npts = p1 - p0;
   const int o0 = a.pt_start[p0], nobs = a.pt_start[p1] - o0;
+#pragma unroll
+  for (int q = 0; q < CPR; ++q) {
+    const int idx = t + TILE * q, rec = idx / CPR, part = idx - rec * CPR;
+    if (rec < nobs) rec_cp16(sP + (size_t)rec * SR + part * EPC, Prec + (size_t)__ldg(slot + o0 + rec) * REC + part * EPC);
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    const int idx = t + TILE * q, rec = idx / 9, c = idx - 9 * rec;
+    if (rec < nobs) rec_cp1<T>(sD + idx, dx_cam + 9 * (size_t)__ldg(a.view + o0 + rec) + c);
+  }
+  rec_commit();
   double acc_e = 0.0, acc_dx = 0.0, acc_jd = 0.0;
   int cam_idx = 0, lp = 0;
+  if (t < nobs) { cam_idx = __ldg(a.view + o0 + t); lp = __ldg(a.point + o0 + t) - p0; }
+  rec_wait<0>();
+  __syncthreads();
   if (t < nobs) {
-    const int i = o0 + t;
-    cam_idx = __ldg(a.view + i);
-    lp = __ldg(a.point + i) - p0;
-    const T* pr = Prec + (size_t)__ldg(slot + i) * REC;
-    T d[9];
+    T r[REC], d[9];
+    lds_rec<0, REC>(sP + (size_t)t * SR, r);
 #pragma unroll
-    for (int b = 0; b < 9; ++b) d[b] = __ldg(dx_cam + 9 * (size_t)cam_idx + b);
+    for (int b = 0; b < 9; ++b) d[b] = sD[9 * t + b];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       T u = T(0);
 #pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        T r0, r1, r2, r3;
-        load4(pr + 12 * k + 4 * g, r0, r1, r2, r3);
-        u += r0 * d[3 * g] + r1 * d[3 * g + 1] + r2 * d[3 * g + 2];
-      }
+      for (int b = 0; b < 9; ++b) u += r[9 * k + b] * d[b];
       su[k][t] = u;
     }
   }
