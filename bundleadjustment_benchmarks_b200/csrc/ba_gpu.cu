@@ -344,7 +344,7 @@ struct Impl : ba_handle {
       for (int ia = pt_start[j]; ia < pt_start[j + 1]; ++ia)
         for (int ib = pt_start[j]; ib < ia; ++ib) {
           const size_t key = (size_t)view[ia] * Wd + (view[ia] - view[ib]);
-          pairs[pos[key]++] = make_int2(slot[ia], slot[ib]);
+          pairs[pos[key]++] = make_int2(ia, ib);  // P records live at the observation index
         }
     { std::vector<int>().swap(cnt); std::vector<int>().swap(pos); }
     // blocks are handed out in (a, b) order: concurrently processed blocks share cameras, so the P records of the
@@ -726,7 +726,7 @@ struct Impl : ba_handle {
     k_cam_update<T><<<1, 1024, 0, stream>>>(N, d_cams.p, d_dx_cam.p, gJvec(), d_cams_test.p, d_scal.p + 4, d_scal.p + 6);
     launches++;
     mark(6);
-    k_backsub_eval<T><<<ntiles, TILE, backsub_smem_bytes<T>(), stream>>>(tile_args(lamT), d_slot.p, d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
+    k_backsub_eval<T><<<ntiles, TILE, backsub_smem_bytes<T>(), stream>>>(tile_args(lamT), d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
                                                     d_partials.p, ntiles);
     launches++;
     CK(cudaGetLastError());

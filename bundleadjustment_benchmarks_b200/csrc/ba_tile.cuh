@@ -278,19 +278,22 @@ __device__ __forceinline__ void tile_phases_123(const TileArgs<T>& a, TileSmem<T
 // synthetic scale) and make S differ from run to run. The structure of S is static (which point
 // contributes to which 9x9 camera-pair block), so it is built once on the host: every non-empty block
 // (a, b), b <= a, owns the list of (observation of a, observation of b) pairs of the points seen by both.
-// Pass 1 (k_point_factor_warp / k_point_factor) stores per observation, at the observation's CAMERA-MAJOR
-// slot (observations sorted by (camera, point)), two records of REC = 28 scalars (224 / 112 bytes):
-//   P record: R12_i = Q1_i^T Jc_i, 3x9 row-major, one pad scalar              (off-diagonal blocks, back-substitution)
-//   D record: Jc_i 2x9 row-major | M_i = I2 - Q1_i Q1_i^T as m00 m01 m11 | w_i = e_i - Q1_i c | e_i | 3 pad
+// Pass 1 (k_point_factor_warp / k_point_factor) stores per observation two records of REC = 28 scalars
+// (224 / 112 bytes):
+//   P record, at the observation's index (point-major, so the back-substitution streams them):
+//             R12_i = Q1_i^T Jc_i, 3x9 row-major, one pad scalar       (off-diagonal blocks, back-substitution)
+//   D record, at the observation's CAMERA-MAJOR slot (observations sorted by (camera, point), so the diagonal
+//             kernel streams a camera's records): Jc_i 2x9 row-major | M_i = I2 - Q1_i Q1_i^T as m00 m01 m11 |
+//             w_i = e_i - Q1_i c | e_i | 3 pad
 //             (diagonal blocks: Jc^T Jc - R12^T R12 = Jc^T M Jc; g: Jc^T e - R12^T c = Jc^T w; gJ = Jc^T e)
 // and per point (R (6), c (3), G = Jp^T e (3), perm, pad) = 16 scalars.
 // Pass 2: k_schur_gather (one warp per off-diagonal block, one LANE per pair with the whole 9x9 block in
 // registers, records staged through shared memory with cp.async one batch of 32 pairs ahead) and
 // k_schur_diag (one CTA per camera streaming the camera's contiguous D records, one lane per record)
 // WRITE the blocks: every entry of S has exactly one writer and a fixed summation order, so the result is
-// bit-reproducible. Camera-major slots keep the working set of consecutive blocks (the records of ~bw
-// cameras) in L2. The back-substitution re-reads the P and point records instead of re-evaluating the
-// Jacobian and the point QR.
+// bit-reproducible. Blocks are processed in (a, b) order, so the P records of the ~bw cameras in flight stay in
+// L2 whatever their storage order. The back-substitution re-reads the P and point records instead of
+// re-evaluating the Jacobian and the point QR.
 //
 // Why one lane per pair: the LSU delivers 128 bytes per clock per SM to the register file, and every
 // distinct 128-byte line touched by a warp instruction costs one pass. With 3x3 register tiles (9 lanes per
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(TILE) k_point_factor(TileArgs<T> a, const int 
 #pragma unroll
     for (int b = 0; b < 27; ++b) rec[b] = sm.R12[b * TP + t];
     rec[27] = T(0);
-    store_rec(Prec + sl * REC, rec);
+    store_rec(Prec + (size_t)(o0 + t) * REC, rec);
 #pragma unroll
     for (int b = 0; b < 18; ++b) rec[b] = sm.Jc[b * TP + t];
     fill_drec_tail<T>(rec, sm.Q[0 * TP + t], sm.Q[1 * TP + t], sm.Q[2 * TP + t], sm.Q[3 * TP + t], sm.Q[4 * TP + t], sm.Q[5 * TP + t],
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(TILE, 4) k_point_factor_warp(TileArgs<T> a, in
 #pragma unroll
     for (int b = 0; b < 9; ++b) rec[9 * k + b] = x[0][k] * jc[b] + x[1][k] * jc[9 + b];
   rec[27] = T(0);
-  store_rec(Prec + sl * REC, rec);
+  store_rec(Prec + (size_t)o * REC, rec);
 #pragma unroll
   for (int b = 0; b < 18; ++b) rec[b] = jc[b];
   fill_drec_tail<T>(rec, x[0][0], x[0][1], x[0][2], x[1][0], x[1][1], x[1][2], cq[0], cq[1], cq[2], e0, e1);
@@ -642,50 +645,68 @@ __global__ void __launch_bounds__(GATHER_THREADS, 1) k_schur_gather(int nblocks,
   extern __shared__ __align__(16) unsigned char gather_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* const wbuf = reinterpret_cast<T*>(gather_smem_raw) + (size_t)warp * 2 * 64 * SR;
-  // batch iterator (warp-uniform state)
-  int t = 0, tend = 0, blk = -1;
-  bool exhausted = false;
-  auto next = [&](int& b_blk, int& b_start, int& b_cnt, bool& b_last) -> bool {
-    if (exhausted) return false;
-    if (t >= tend) {
-      int bi = 0;
-      if (lane == 0) bi = atomicAdd(counter, 1);
-      bi = __shfl_sync(FULL, bi, 0);
-      if (bi >= nblocks) { exhausted = true; return false; }
-      blk = bi; t = __ldg(blk_start + bi); tend = __ldg(blk_start + bi + 1);
-    }
-    b_blk = blk; b_start = t; b_cnt = min(32, tend - t); t += b_cnt; b_last = (t >= tend);
-    return true;
+  // Three-deep software pipeline per warp (a warp issues in order, so a load only costs its latency when its
+  // first consumer is reached): while batch i is multiplied, the records of batch i+1 are in flight and the
+  // pair indices of batch i+2 are being loaded; the NEXT block's id (global counter) and pair range are
+  // fetched when the current block is entered. r1 v6 consumed each of these right after issuing it: 30 % of
+  // all stall samples sat on the first shuffle after the pair-index load.
+  struct Batch { int blk, start, cnt; bool last, valid; int2 pr; };
+  int t = 0, tend = 0, blk = -1;          // current block: id, next pair, end of its pair range
+  int nb_id = 0, nb_t = 0, nb_end = 0;    // prefetched next block
+  auto fetch_block = [&]() {              // start fetching the warp's next block (nothing is consumed here)
+    int bi = 0;
+    if (lane == 0) bi = atomicAdd(counter, 1);
+    bi = __shfl_sync(FULL, bi, 0);
+    nb_id = bi;
+    const int bc = min(bi, nblocks - 1);
+    nb_t = __ldg(blk_start + bc); nb_end = __ldg(blk_start + bc + 1);
   };
-  // records of the batch -> buf: slots 0..31 the a-records of the pairs, slots 32..63 the b-records
-  auto issue = [&](const int start, const int cnt, T* buf) {
-    int2 pr = make_int2(0, 0);
-    if (lane < cnt) pr = __ldg(pairs + start + lane);
+  auto next = [&]() -> Batch {
+    Batch o; o.valid = false; o.blk = 0; o.start = 0; o.cnt = 0; o.last = false; o.pr = make_int2(0, 0);
+    if (t >= tend) {
+      if (nb_id >= nblocks) return o;
+      blk = nb_id; t = nb_t; tend = nb_end;
+      fetch_block();
+    }
+    o.valid = true; o.blk = blk; o.start = t; o.cnt = min(32, tend - t); t += o.cnt; o.last = (t >= tend);
+    if (lane < o.cnt) o.pr = __ldg(pairs + o.start + lane);
+    return o;
+  };
+  // records of a batch -> buf: slots 0..31 the a-records of the pairs, slots 32..63 the b-records. One
+  // instruction copies RPI whole records (lane = (record, 16-byte chunk)), so the address arithmetic per copy
+  // is one shuffle and one multiply-add.
+  constexpr int RPI = 32 / CPR, NQ = 32 / RPI;
+  const int rsub = lane / CPR, part = lane - rsub * CPR;
+  const bool cpl = lane < RPI * CPR;
+  const T* const src_lane = Prec + part * EPC;
+  const int dst_lane = rsub * SR + part * EPC;
+  auto issue = [&](const Batch& bt, T* buf) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
-      for (int q = 0; q < CPR; ++q) {
-        const int idx = lane + 32 * q, rec = idx / CPR, part = idx - rec * CPR;
-        const int sl = __shfl_sync(FULL, h ? pr.y : pr.x, rec);
-        if (rec < cnt) rec_cp16(buf + (size_t)(32 * h + rec) * SR + part * EPC, Prec + (size_t)sl * REC + part * EPC);
+      for (int q = 0; q < NQ; ++q) {
+        const int rec = RPI * q + rsub;
+        const int sl = __shfl_sync(FULL, h ? bt.pr.y : bt.pr.x, rec & 31);
+        if (cpl && rec < bt.cnt) rec_cp16(buf + dst_lane + (32 * h + RPI * q) * SR, src_lane + (size_t)sl * REC);
       }
     }
   };
   T acc[81];
 #pragma unroll
   for (int e = 0; e < 81; ++e) acc[e] = T(0);
-  int c_blk = 0, c_start = 0, c_cnt = 0; bool c_last = false;
-  bool have = next(c_blk, c_start, c_cnt, c_last);
-  if (have) issue(c_start, c_cnt, wbuf);
+  fetch_block();
+  Batch c = next();
+  if (c.valid) issue(c, wbuf);
   rec_commit();
+  Batch nx = next();
   int cur = 0;
-  while (have) {
-    int n_blk = 0, n_start = 0, n_cnt = 0; bool n_last = false;
-    const bool have_n = next(n_blk, n_start, n_cnt, n_last);
-    if (have_n) issue(n_start, n_cnt, wbuf + (size_t)(cur ^ 1) * 64 * SR);
+  while (c.valid) {
+    if (nx.valid) issue(nx, wbuf + (size_t)(cur ^ 1) * 64 * SR);
     rec_commit();
+    Batch nn = next();   // pair indices of the batch after next: consumed one iteration later
     rec_wait<1>();
     __syncwarp();
+    const int c_cnt = c.cnt, c_blk = c.blk; const bool c_last = c.last;
     T* const buf = wbuf + (size_t)cur * 64 * SR;
     if (lane < c_cnt) {
       const T* pa = buf + (size_t)lane * SR;
@@ -733,7 +754,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 1) k_schur_gather(int nblocks,
 #pragma unroll
       for (int e = 0; e < 81; ++e) acc[e] = T(0);
     }
-    c_blk = n_blk; c_start = n_start; c_cnt = n_cnt; c_last = n_last; have = have_n;
+    c = nx; nx = nn;
     cur ^= 1;
   }
   rec_wait<0>();
@@ -861,35 +882,69 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_schur_diag(const int* __res
 template <class T> constexpr size_t backsub_smem_bytes() { return (size_t)TILE * (RecGeom<T>::SREC + 9) * sizeof(T); }
 
 template <class T>
-__global__ void __launch_bounds__(TILE) k_backsub_eval(TileArgs<T> a, const int* __restrict__ slot, const T* __restrict__ Prec,
-                                                       const T* __restrict__ Ptrec, const T* __restrict__ dx_cam, const T* __restrict__ cams_test,
-                                                       T* __restrict__ dx_pt, T* __restrict__ X_test, double* __restrict__ partials, int ntiles) {
+__global__ void __launch_bounds__(TILE, 5) k_backsub_eval(TileArgs<T> a, const T* __restrict__ Prec,
+                                                          const T* __restrict__ Ptrec, const T* __restrict__ dx_cam, const T* __restrict__ cams_test,
+                                                          T* __restrict__ dx_pt, T* __restrict__ X_test, double* __restrict__ partials, int ntiles) {
+  constexpr unsigned FULL = 0xffffffffu;
   constexpr int EPC = RecGeom<T>::EPC, CPR = RecGeom<T>::CPR, SR = RecGeom<T>::SREC;
+  constexpr int RPI = 32 / CPR, NQ = 32 / RPI;
   extern __shared__ __align__(16) unsigned char backsub_smem_raw[];
   T* const sP = reinterpret_cast<T*>(backsub_smem_raw);  // [TILE][SR]
   T* const sD = sP + (size_t)TILE * SR;                  // [TILE][9]
   __shared__ T su[3][TP];
   __shared__ T sx[3][TP];
   __shared__ double red[3 * (TILE / 32)];
-  const int t = threadIdx.x, tile = blockIdx.x;
-  const int p0 = a.tile_pt[tile], p1 = a.tile_pt[tile + 1], npts = p1 - p0;
-  const int o0 = a.pt_start[p0], nobs = a.pt_start[p1] - o0;
+  const int t = threadIdx.x, tile = blockIdx.x, lane = t & 31, w0 = t & ~31;
+  const int p0 = __ldg(a.tile_pt + tile), p1 = __ldg(a.tile_pt + tile + 1), npts = p1 - p0;
+  const int o0 = __ldg(a.pt_start + p0), nobs = __ldg(a.pt_start + p1) - o0;
+  // Every warp stages the records and dx_cam rows of ITS 32 observations (lane = (record, chunk): one copy
+  // instruction moves RPI whole records; the tile's records are contiguous), so a __syncwarp suffices before
+  // they are read. Every load that does not depend on staged data is issued before the wait: the kernel is a
+  // chain of dependent global loads (tile -> point range -> cameras -> dx_cam) and nothing else may add a level.
+  {
+    const int rsub = lane / CPR, part = lane - rsub * CPR;
+    if (lane < RPI * CPR) {
 #pragma unroll
-  for (int q = 0; q < CPR; ++q) {
-    const int idx = t + TILE * q, rec = idx / CPR, part = idx - rec * CPR;
-    if (rec < nobs) rec_cp16(sP + (size_t)rec * SR + part * EPC, Prec + (size_t)__ldg(slot + o0 + rec) * REC + part * EPC);
+      for (int q = 0; q < NQ; ++q) {
+        const int rec = w0 + RPI * q + rsub;
+        if (rec < nobs) rec_cp16(sP + (size_t)rec * SR + part * EPC, Prec + (size_t)(o0 + rec) * REC + part * EPC);
+      }
+    }
   }
+  int cam_idx = 0, lp = 0;
+  if (t < nobs) { cam_idx = __ldg(a.view + o0 + t); lp = __ldg(a.point + o0 + t) - p0; }
+  {
+    const int r9 = lane / 9, c9 = lane - 9 * r9;
 #pragma unroll
-  for (int q = 0; q < 9; ++q) {
-    const int idx = t + TILE * q, rec = idx / 9, c = idx - 9 * rec;
-    if (rec < nobs) rec_cp1<T>(sD + idx, dx_cam + 9 * (size_t)__ldg(a.view + o0 + rec) + c);
+    for (int q = 0; q < 11; ++q) {
+      const int rl = 3 * q + r9;                       // observation within the warp
+      const int cam = __shfl_sync(FULL, cam_idx, rl & 31);
+      if (lane < 27 && rl < 32 && w0 + rl < nobs) rec_cp1<T>(sD + 9 * (w0 + rl) + c9, dx_cam + 9 * (size_t)cam + c9);
+    }
   }
   rec_commit();
   double acc_e = 0.0, acc_dx = 0.0, acc_jd = 0.0;
-  int cam_idx = 0, lp = 0;
-  if (t < nobs) { cam_idx = __ldg(a.view + o0 + t); lp = __ldg(a.point + o0 + t) - p0; }
+  int lo = 0, n = 0;
+  T m0 = T(0), m1 = T(0);
+  T R00 = T(1), R01 = T(0), R02 = T(0), R11 = T(1), R12v = T(0), R22 = T(1), c0 = T(0), c1 = T(0), c2 = T(0), G0 = T(0), G1 = T(0), G2 = T(0), pf = T(0);
+  T X0 = T(0), X1 = T(0), X2 = T(0);
+  Cam<T> cam;
+  if (t < nobs) { m0 = __ldg(a.meas + 2 * (size_t)(o0 + t)); m1 = __ldg(a.meas + 2 * (size_t)(o0 + t) + 1); }
+  const size_t gp = 3 * (size_t)(p0 + t);
+  if (t < npts) {
+    const int ps = __ldg(a.pt_start + p0 + t);
+    lo = ps - o0; n = __ldg(a.pt_start + p0 + t + 1) - ps;
+    const T* q = Ptrec + (size_t)(p0 + t) * PREC;
+    T z_, z1_, z2_;
+    load4(q, R00, R01, R02, R11);
+    load4(q + 4, R12v, R22, c0, c1);
+    load4(q + 8, c2, G0, G1, G2);
+    load4(q + 12, pf, z_, z1_, z2_);
+    X0 = __ldg(a.X + gp); X1 = __ldg(a.X + gp + 1); X2 = __ldg(a.X + gp + 2);
+  }
+  load_cam<T>(cams_test, cam_idx, cam);
   rec_wait<0>();
-  __syncthreads();
+  __syncwarp();
   if (t < nobs) {
     T r[REC], d[9];
     lds_rec<0, REC>(sP + (size_t)t * SR, r);
@@ -905,13 +960,6 @@ __global__ void __launch_bounds__(TILE) k_backsub_eval(TileArgs<T> a, const int*
   }
   __syncthreads();
   if (t < npts) {
-    const int lo = a.pt_start[p0 + t] - o0, n = a.pt_start[p0 + t + 1] - a.pt_start[p0 + t];
-    const T* q = Ptrec + (size_t)(p0 + t) * PREC;
-    T R00, R01, R02, R11, R12v, R22, c0, c1, c2, G0, G1, G2, pf, z_, z1_, z2_;
-    load4(q, R00, R01, R02, R11);
-    load4(q + 4, R12v, R22, c0, c1);
-    load4(q + 8, c2, G0, G1, G2);
-    load4(q + 12, pf, z_, z1_, z2_);
     T r0 = -c0, r1 = -c1, r2 = -c2;
     for (int i = 0; i < n; ++i) { r0 -= su[0][lo + i]; r1 -= su[1][lo + i]; r2 -= su[2][lo + i]; }
     const T z2 = r2 / R22;
@@ -920,21 +968,17 @@ __global__ void __launch_bounds__(TILE) k_backsub_eval(TileArgs<T> a, const int*
     const int pm = (int)pf;
     T d[3];
     d[pm & 3] = z0; d[(pm >> 2) & 3] = z1; d[(pm >> 4) & 3] = z2;
-    const size_t gp = 3 * (size_t)(p0 + t);
     acc_dx += (double)(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     acc_jd += (double)(G0 * d[0] + G1 * d[1] + G2 * d[2]);
     dx_pt[gp] = d[0]; dx_pt[gp + 1] = d[1]; dx_pt[gp + 2] = d[2];
-    const T x0 = __ldg(a.X + gp) + d[0], x1 = __ldg(a.X + gp + 1) + d[1], x2 = __ldg(a.X + gp + 2) + d[2];
+    const T x0 = X0 + d[0], x1 = X1 + d[1], x2 = X2 + d[2];
     X_test[gp] = x0; X_test[gp + 1] = x1; X_test[gp + 2] = x2;
     sx[0][t] = x0; sx[1][t] = x1; sx[2][t] = x2;
   }
   __syncthreads();
   if (t < nobs) {
-    Cam<T> c; load_cam<T>(cams_test, cam_idx, c);
-    const int i = o0 + t;
-    const T m0 = __ldg(a.meas + 2 * (size_t)i), m1 = __ldg(a.meas + 2 * (size_t)i + 1);
     T e0, e1;
-    obs_residual<T>(c, sx[0][lp], sx[1][lp], sx[2][lp], m0, m1, a.tau2, e0, e1);
+    obs_residual<T>(cam, sx[0][lp], sx[1][lp], sx[2][lp], m0, m1, a.tau2, e0, e1);
     acc_e += (double)(e0 * e0 + e1 * e1);
   }
 #pragma unroll
@@ -943,7 +987,7 @@ __global__ void __launch_bounds__(TILE) k_backsub_eval(TileArgs<T> a, const int*
     acc_dx += __shfl_down_sync(0xffffffffu, acc_dx, off);
     acc_jd += __shfl_down_sync(0xffffffffu, acc_jd, off);
   }
-  const int lane = t & 31, warp = t >> 5;
+  const int warp = t >> 5;
   if (lane == 0) { red[warp] = acc_e; red[TILE / 32 + warp] = acc_dx; red[2 * (TILE / 32) + warp] = acc_jd; }
   __syncthreads();
   if (t < 3) {
