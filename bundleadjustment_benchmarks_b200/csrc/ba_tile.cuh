@@ -528,8 +528,11 @@ __device__ __forceinline__ void seg_normal(T (&x)[2][3], const T e0, const T e1,
   seg_sum<T, 3>(cq, s0, n, nmax, i);
 }
 
+#ifndef BA_PF_MIN_BLOCKS
+#define BA_PF_MIN_BLOCKS 4
+#endif
 template <class T>
-__global__ void __launch_bounds__(TILE, 4) k_point_factor_warp(TileArgs<T> a, int nunits, const int* __restrict__ unit_pt, const int* __restrict__ slot,
+__global__ void __launch_bounds__(TILE, BA_PF_MIN_BLOCKS) k_point_factor_warp(TileArgs<T> a, int nunits, const int* __restrict__ unit_pt, const int* __restrict__ slot,
                                                             T* __restrict__ Prec, T* __restrict__ Drec, T* __restrict__ Ptrec) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, u = blockIdx.x * (TILE / 32) + (threadIdx.x >> 5);
@@ -634,7 +637,8 @@ template <int LO, int HI> __device__ __forceinline__ void lds_rec(const float* s
 // ---------------------------------------------------------------------------------------------
 constexpr int GATHER_WARPS = 6;
 constexpr int GATHER_THREADS = 32 * GATHER_WARPS;
-template <class T> constexpr size_t gather_smem_bytes() { return (size_t)GATHER_WARPS * 2 * 64 * RecGeom<T>::SREC * sizeof(T); }
+template <class T> constexpr size_t gather_rec_bytes() { return (size_t)GATHER_WARPS * 2 * 64 * RecGeom<T>::SREC * sizeof(T); }
+template <class T> constexpr size_t gather_smem_bytes() { return gather_rec_bytes<T>() + (size_t)GATHER_WARPS * 2 * 32 * sizeof(int2); }
 
 template <class T>
 __global__ void __launch_bounds__(GATHER_THREADS, 1) k_schur_gather(int nblocks, const int* __restrict__ blk_a, const int* __restrict__ blk_b,
@@ -645,32 +649,40 @@ __global__ void __launch_bounds__(GATHER_THREADS, 1) k_schur_gather(int nblocks,
   extern __shared__ __align__(16) unsigned char gather_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* const wbuf = reinterpret_cast<T*>(gather_smem_raw) + (size_t)warp * 2 * 64 * SR;
-  // Three-deep software pipeline per warp (a warp issues in order, so a load only costs its latency when its
-  // first consumer is reached): while batch i is multiplied, the records of batch i+1 are in flight and the
-  // pair indices of batch i+2 are being loaded; the NEXT block's id (global counter) and pair range are
-  // fetched when the current block is entered. r1 v6 consumed each of these right after issuing it: 30 % of
-  // all stall samples sat on the first shuffle after the pair-index load.
-  struct Batch { int blk, start, cnt; bool last, valid; int2 pr; };
-  int t = 0, tend = 0, blk = -1;          // current block: id, next pair, end of its pair range
-  int nb_id = 0, nb_t = 0, nb_end = 0;    // prefetched next block
-  auto fetch_block = [&]() {              // start fetching the warp's next block (nothing is consumed here)
-    int bi = 0;
-    if (lane == 0) bi = atomicAdd(counter, 1);
-    bi = __shfl_sync(FULL, bi, 0);
-    nb_id = bi;
-    const int bc = min(bi, nblocks - 1);
-    nb_t = __ldg(blk_start + bc); nb_end = __ldg(blk_start + bc + 1);
+  // Three-deep software pipeline per warp. A warp issues in order, so a load costs its latency when its first
+  // consumer is reached, and a register MOVE of a loaded value is a consumer (r1 v6: 30 % of all stall samples sat
+  // on the first use of the pair indices, then on the loop-carried copy of them). Therefore nothing loaded is
+  // carried in registers across iterations: while batch i is multiplied, the records of batch i+1 are in flight
+  // into the other staging buffer and the pair indices of batch i+2 into a two-slot shared-memory ring (both
+  // cp.async, one commit group per iteration); block ids are drawn from the global counter two blocks ahead and
+  // the pair ranges one block ahead.
+  struct Batch { int blk, start, cnt, ca, cb; bool last, valid; };
+  int2* const ring = reinterpret_cast<int2*>(gather_smem_raw + (size_t)GATHER_WARPS * 2 * 64 * SR * sizeof(T)) + warp * 64;  // [2][32]
+  int t = 0, tend = 0, blk = -1, ca = 0, cb = 0;   // current block: next pair, end of its pair range, id, cameras
+  int id1 = 0, t1 = 0, end1 = 0, ca1 = 0, cb1 = 0; // next block (id resolved; range/cameras loading)
+  int id2 = 0;                                     // block after next: counter value in flight (lane 0)
+  auto draw = [&]() { if (lane == 0) id2 = atomicAdd(counter, 1); };
+  auto load_next_block = [&]() {                   // consumes id2 (drawn one block ago), starts the range loads
+    id1 = __shfl_sync(FULL, id2, 0);
+    const int bc = min(id1, nblocks - 1);
+    t1 = __ldg(blk_start + bc); end1 = __ldg(blk_start + bc + 1); ca1 = __ldg(blk_a + bc); cb1 = __ldg(blk_b + bc);
+    draw();
   };
   auto next = [&]() -> Batch {
-    Batch o; o.valid = false; o.blk = 0; o.start = 0; o.cnt = 0; o.last = false; o.pr = make_int2(0, 0);
+    Batch o; o.valid = false; o.blk = 0; o.start = 0; o.cnt = 0; o.last = false; o.ca = 0; o.cb = 0;
     if (t >= tend) {
-      if (nb_id >= nblocks) return o;
-      blk = nb_id; t = nb_t; tend = nb_end;
-      fetch_block();
+      if (id1 >= nblocks) return o;
+      blk = id1; t = t1; tend = end1; ca = ca1; cb = cb1;
+      load_next_block();
     }
-    o.valid = true; o.blk = blk; o.start = t; o.cnt = min(32, tend - t); t += o.cnt; o.last = (t >= tend);
-    if (lane < o.cnt) o.pr = __ldg(pairs + o.start + lane);
+    o.valid = true; o.blk = blk; o.start = t; o.cnt = min(32, tend - t); t += o.cnt; o.last = (t >= tend); o.ca = ca; o.cb = cb;
     return o;
+  };
+  auto issue_pairs = [&](const Batch& bt, int2* slot) {
+    if (bt.valid && lane < bt.cnt) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(slot + lane);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(pairs + bt.start + lane) : "memory");
+    }
   };
   // records of a batch -> buf: slots 0..31 the a-records of the pairs, slots 32..63 the b-records. One
   // instruction copies RPI whole records (lane = (record, 16-byte chunk)), so the address arithmetic per copy
@@ -680,13 +692,16 @@ __global__ void __launch_bounds__(GATHER_THREADS, 1) k_schur_gather(int nblocks,
   const bool cpl = lane < RPI * CPR;
   const T* const src_lane = Prec + part * EPC;
   const int dst_lane = rsub * SR + part * EPC;
-  auto issue = [&](const Batch& bt, T* buf) {
+  auto issue_records = [&](const Batch& bt, const int2* slot, T* buf) {
+    if (!bt.valid) return;
+    int2 pr = make_int2(0, 0);
+    if (lane < bt.cnt) pr = slot[lane];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int rec = RPI * q + rsub;
-        const int sl = __shfl_sync(FULL, h ? bt.pr.y : bt.pr.x, rec & 31);
+        const int sl = __shfl_sync(FULL, h ? pr.y : pr.x, rec & 31);
         if (cpl && rec < bt.cnt) rec_cp16(buf + dst_lane + (32 * h + RPI * q) * SR, src_lane + (size_t)sl * REC);
       }
     }
@@ -694,19 +709,26 @@ __global__ void __launch_bounds__(GATHER_THREADS, 1) k_schur_gather(int nblocks,
   T acc[81];
 #pragma unroll
   for (int e = 0; e < 81; ++e) acc[e] = T(0);
-  fetch_block();
+  draw();
+  load_next_block();
   Batch c = next();
-  if (c.valid) issue(c, wbuf);
+  issue_pairs(c, ring);
   rec_commit();
   Batch nx = next();
+  rec_wait<0>();
+  __syncwarp();
+  issue_records(c, ring, wbuf);
+  issue_pairs(nx, ring + 32);
+  rec_commit();
   int cur = 0;
   while (c.valid) {
-    if (nx.valid) issue(nx, wbuf + (size_t)(cur ^ 1) * 64 * SR);
-    rec_commit();
-    Batch nn = next();   // pair indices of the batch after next: consumed one iteration later
-    rec_wait<1>();
+    rec_wait<0>();      // records of this batch and pair indices of the next one have landed
     __syncwarp();
-    const int c_cnt = c.cnt, c_blk = c.blk; const bool c_last = c.last;
+    issue_records(nx, ring + 32 * (cur ^ 1), wbuf + (size_t)(cur ^ 1) * 64 * SR);
+    const Batch nn = next();
+    issue_pairs(nn, ring + 32 * cur);
+    rec_commit();
+    const int c_cnt = c.cnt; const bool c_last = c.last;
     T* const buf = wbuf + (size_t)cur * 64 * SR;
     if (lane < c_cnt) {
       const T* pa = buf + (size_t)lane * SR;
@@ -734,7 +756,7 @@ __global__ void __launch_bounds__(GATHER_THREADS, 1) k_schur_gather(int nblocks,
     __syncwarp();
     if (c_last) {
       // fixed-order sum over the 32 lanes, 27 entries at a time, through the (consumed) staging buffer
-      const int ca = __ldg(blk_a + c_blk), cb = __ldg(blk_b + c_blk);
+      const int ca = c.ca, cb = c.cb;
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
 #pragma unroll
