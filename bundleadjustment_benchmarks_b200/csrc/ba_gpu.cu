@@ -405,6 +405,7 @@ struct Impl : ba_handle {
     if (const char* ts = std::getenv("BA_LDLT_TWOSIDED")) two_sided = atoi(ts) != 0;
     CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterSmem<T>)));
     CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CK(cudaFuncSetAttribute(k_band_qr_backsolve_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     for (; cluster_size > 1; cluster_size /= 2) {  // largest cluster the device can co-schedule
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(cluster_size); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = sizeof(ClusterSmem<T>);
@@ -679,14 +680,15 @@ struct Impl : ba_handle {
     launches++;
     CK(cudaGetLastError());
     QRMat<T> Q{G, ld, n, kd, ku};
-    void* args[] = {&Q, &tauv, &rhs};
+    long long* dbgp = d_dbg.p;
+    void* args[] = {&Q, &tauv, &rhs, &dbgp};
     if (kd + QR_PB <= 32 * QR_MAXR) {  // banded case: reflectors in shared memory, columns in registers
-      const size_t smem = ((size_t)QR_PB * (kd + QR_PB) + QR_PB + QR_THREADS / 32 + 2) * sizeof(T);
+      const size_t smem = QrSmem<T>::bytes(kd);
       CK(cudaFuncSetAttribute(k_band_qr_reg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int occ = 0, sms = 0;
       CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_qr_reg<T>, QR_THREADS, smem));
-      const int want = (std::min(n - 1, 2 * kd) + 1 + QR_THREADS / 32 - 1) / (QR_THREADS / 32);  // one warp per trailing column
+      const int want = 1 + (std::min(n - 1, 2 * kd) + 1 + QR_THREADS / 32 - 1) / (QR_THREADS / 32);  // panel CTA + one warp per trailing column
       const int grid = std::max(1, std::min(std::max(occ, 1) * sms, want));
       CK(cudaLaunchCooperativeKernel((void*)k_band_qr_reg<T>, dim3(grid), dim3(QR_THREADS), args, smem, stream));
     } else {
@@ -709,7 +711,17 @@ struct Impl : ba_handle {
       const size_t ld = (size_t)kd + ku + 1;
       T* G = d_qr.p; T* rhs = d_qr.p + (size_t)n * ld + n;
       QRMat<T> Q{G, ld, n, kd, ku};
-      k_band_qr_backsolve<T><<<1, QR_SOLVE_THREADS, 0, stream>>>(Q, rhs, d_dx_cam.p, T(-1));
+      if (cluster_size >= 2 && !std::getenv("BA_QR_SOLVE_1CTA")) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cluster_size); cfg.blockDim = dim3(QRS_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_band_qr_backsolve_cluster<T>, Q, rhs, d_dx_cam.p, T(-1)));
+      } else {
+        k_band_qr_backsolve<T><<<1, QR_SOLVE_THREADS, 0, stream>>>(Q, rhs, d_dx_cam.p, T(-1));
+      }
       launches++;
     }
     return BA_OK;
