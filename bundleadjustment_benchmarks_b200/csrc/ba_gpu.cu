@@ -674,14 +674,14 @@ struct Impl : ba_handle {
   int qr_factor() {
     const int ku = std::min(n - 1, 2 * kd);
     const size_t ld = (size_t)kd + ku + 1;
-    if (d_qr.n < (size_t)n * ld + 2 * (size_t)n) CK(d_qr.alloc((size_t)n * ld + 2 * (size_t)n));
-    T* G = d_qr.p; T* tauv = d_qr.p + (size_t)n * ld; T* rhs = tauv + n;
+    if (d_qr.n < (size_t)n * ld + 2 * (size_t)n + 128) CK(d_qr.alloc((size_t)n * ld + 2 * (size_t)n + 128));
+    T* G = d_qr.p; T* tauv = d_qr.p + (size_t)n * ld; T* rhs = tauv + n; T* Tg2 = rhs + n;  // Tg2: T of the current / next panel
     k_band_expand<T><<<std::min<size_t>(((size_t)n * ld + 255) / 256, 65535), 256, 0, stream>>>(band(), G, ld, ku, gvec(), rhs);
     launches++;
     CK(cudaGetLastError());
     QRMat<T> Q{G, ld, n, kd, ku};
     long long* dbgp = d_dbg.p;
-    void* args[] = {&Q, &tauv, &rhs, &dbgp};
+    void* args[] = {&Q, &tauv, &rhs, &Tg2, &dbgp};
     if (kd + QR_PB <= 32 * QR_MAXR) {  // banded case: reflectors in shared memory, columns in registers
       const size_t smem = QrSmem<T>::bytes(kd);
       CK(cudaFuncSetAttribute(k_band_qr_reg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

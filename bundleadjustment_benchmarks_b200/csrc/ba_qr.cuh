@@ -144,169 +144,312 @@ __global__ void __launch_bounds__(QR_THREADS) k_band_qr(QRMat<T> Q, T* __restric
 // ---------------------------------------------------------------------------------------------
 constexpr int QR_MAXR = 20;  // rows per lane held in registers
 constexpr int QR_RPT = (32 * QR_MAXR + QR_THREADS - 1) / QR_THREADS;  // panel rows per thread in the panel factorisation
+static_assert(QR_PB == 8 && QR_THREADS == 256, "the reductions of the panel kernel are written for 8-column panels and 8 warps");
 
-// Look-ahead: CTA 0 is the PANEL CTA. In iteration k it gives the columns of panel k+1 panel k's update and
-// factors panel k+1 in shared memory while every other CTA updates the remaining trailing columns (and the
-// right-hand side) with panel k; ONE grid barrier per panel. The panel factorisation needs one block barrier
-// per column: a single pass over the column accumulates |tail|^2 AND the dot products with the remaining
-// panel columns (they do not depend on beta), every thread then derives beta / tau redundantly, and the
-// second pass scales the reflector and updates the remaining columns on rows the thread owns.
-// r1 v4 (panel factored between two grid barriers, five block barriers and a one-thread scalar step per
-// column): 41 us per 8-column panel.
+// Look-ahead + compact WY. CTA 0 is the PANEL CTA: in iteration k it gives the columns of panel k+1 panel k's
+// update and factors panel k+1 in shared memory while every other CTA updates the remaining trailing columns
+// (and the right-hand side) with panel k; ONE grid barrier per panel.
+//  * Panel factorisation, one block barrier per column: a single pass over the column accumulates |tail|^2, the
+//    dot products with the remaining panel columns (they do not depend on beta) and the dot products with the
+//    previous reflectors (for T); every thread then derives beta / tau redundantly; the second pass scales the
+//    reflector and updates the remaining columns on rows the thread owns.
+//  * The panel's reflectors are applied as Q^T x = x - V (T^T (V^T x)) (T: 8x8 upper triangular, dlarft
+//    recurrence): the 8 dot products of a column are independent, so the warp does ONE reduction per column
+//    instead of eight dependent ones, and one warp carries two columns so that V is read once for both.
+// r1 v4 (panel factored between two grid barriers, five block barriers and a one-thread scalar step per column,
+// reflectors applied one by one): 41 us per 8-column panel; r1 v6 with look-ahead only: 24.7 us
+// (profiles/r01_dense_notes.md: apply 6.4 us, panel 16.3 us).
+constexpr int QR_WS = 16 * 33 + 16;   // per-warp scratch of qr_apply_wy: partial dots [16][33] + z [16]
 template <class T>
 struct QrSmem {
-  // dynamic layout: sV[QR_PB][LV] reflectors of the current panel | sP[QR_PB][LV] panel being factored (CTA 0) |
-  // stau[QR_PB] | spart[2][QR_THREADS/32][QR_PB + 1]
-  static size_t bytes(int kd) { return ((size_t)2 * QR_PB * (kd + QR_PB) + QR_PB + 2 * (QR_THREADS / 32) * (QR_PB + 1)) * sizeof(T); }
+  // dynamic layout: sV[QR_PB][LV] | sP[QR_PB][LV] | sT[64] | sTn[64] | spart[2][64] | sG[64] | ws[8][QR_WS]
+  static size_t bytes(int kd) { return ((size_t)2 * QR_PB * (kd + QR_PB) + 5 * 64 + (QR_THREADS / 32) * QR_WS) * sizeof(T); }
 };
 
-// apply the pb reflectors staged in sV (v(col) = 1 implicit, sV[c][r] valid for r > c) to one column / the rhs
-template <class T>
-__device__ __forceinline__ void qr_apply_panel(const QRMat<T>& Q, const T* __restrict__ sV, const T* __restrict__ stau, const int LV, const int k0,
-                                               const int pb, const int j, T* __restrict__ xp, const int rlo, const int rlast, const bool is_rhs,
-                                               const int lane, T* __restrict__ sdst = nullptr, const int sbase = 0) {
-  T x[QR_MAXR];
+// Reduce-scatter over the warp followed by a butterfly on the surviving entry: on return every lane holds the warp
+// total of entry (lane >> (5 - LOG)) & (NV - 1); NV - 1 + (5 - LOG) shuffles instead of 5 NV.
+template <class T, int NV, int LOG>
+__device__ __forceinline__ T warp_reduce_scatter(T (&v)[NV], const int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
 #pragma unroll
-  for (int t = 0; t < QR_MAXR; ++t) { const int i = k0 + lane + 32 * t; x[t] = (i >= rlo && i <= rlast) ? xp[i] : T(0); }
-  for (int c = 0; c < pb; ++c) {
-    const int col = k0 + c;
-    const T tau = stau[c];
-    if ((!is_rhs && j > col + Q.ku) || tau == T(0)) continue;
-    const T* v = sV + c * LV;
-    T d = T(0);
+  for (int st = 0; st < LOG; ++st) {
+    const int h = NV >> (st + 1), off = 16 >> st;
+    const bool upper = (lane & off) != 0;
 #pragma unroll
-    for (int t = 0; t < QR_MAXR; ++t) { const int r = lane + 32 * t; if (r < LV) d += v[r] * x[t]; }  // v[r] = 0 for r <= c and beyond the column
-    d = warp_sum(d);
-    const T xcol = __shfl_sync(0xffffffffu, x[0], c);  // x(col): local row c (< QR_PB <= 32) lives in lane c, register 0
-    d = (d + xcol) * tau;
-#pragma unroll
-    for (int t = 0; t < QR_MAXR; ++t) { const int r = lane + 32 * t; if (r < LV) x[t] -= d * v[r]; }
-    if (lane == c) x[0] -= d;
+    for (int i = 0; i < NV / 2; ++i) {
+      if (i < h) {
+        const T send = upper ? v[i] : v[i + h];
+        const T recv = __shfl_xor_sync(FULL, send, off);
+        v[i] = (upper ? v[i + h] : v[i]) + recv;
+      }
+    }
   }
-  // rows >= sbase of a next-panel column go to the panel CTA's shared-memory panel (they are rewritten by the panel
-  // write-back anyway); the rows above are final entries of R
+#pragma unroll
+  for (int off = 16 >> LOG; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(FULL, v[0], off);
+  return v[0];
+}
+
+// Householder scalars from the leading entry c0 and |tail|^2 (valid: tail2 > tiny): beta = -sign(c0) |x|,
+// inv = 1 / (c0 - beta), tau = (beta - c0) / beta = 1 - c0 / beta. Double: rsqrt + reciprocal seeds with
+// FMA corrections (a dependent chain of ~100 cycles instead of the ~400 of sqrt and two IEEE divisions in
+// sequence; relative error ~1e-16, which perturbs the reflector within its own rounding error).
+__device__ __forceinline__ void householder_scalars(const double c0, const double tail2, double& beta, double& inv, double& tau) {
+  const double a = fma(c0, c0, tail2);
+  double r = rsqrt(a);                       // 1 / |x|
+  const double nb0 = a * r;
+  const double nb = fma(fma(-nb0, nb0, a), 0.5 * r, nb0);  // one Newton step on sqrt(a)
+  r = fma(fma(-nb, r, 1.0), r, r);           // and on its reciprocal
+  beta = (c0 >= 0.0) ? -nb : nb;
+  const double rb = (c0 >= 0.0) ? -r : r;    // 1 / beta
+  inv = pivot_rcp(c0 - beta);
+  tau = fma(-c0, rb, 1.0);
+}
+__device__ __forceinline__ void householder_scalars(const float c0, const float tail2, float& beta, float& inv, float& tau) {
+  beta = sqrtf(c0 * c0 + tail2);
+  if (c0 >= 0.0f) beta = -beta;
+  inv = 1.0f / (c0 - beta);
+  tau = (beta - c0) / beta;
+}
+
+// Apply the panel staged in sV (unit diagonal, zeros above; zero beyond each column's band) and sT to two columns
+// (or one: xp1 == nullptr). x(r) = xp[r]; rows [rlo, rlast]; rows >= sbase go to sdst (panel CTA) instead of xp.
+// The loops over the 8 reflectors are ROLLED (2 KB of code; fully unrolled the function was 44 KB and the kernel
+// instruction-fetch bound): pass 1 leaves the per-lane partial dot products in the warp's scratch, 16 lanes sum
+// them, z = T^T w by shuffles, pass 2 subtracts V z.
+template <class T>
+__device__ __noinline__ void qr_apply_wy(const T* __restrict__ sV, const T* __restrict__ sT, T* __restrict__ ws, const int LV, const int k0,
+                                         const int rlast, T* __restrict__ xp0, const int rlo0, T* __restrict__ xp1, const int rlo1, const int lane,
+                                         T* __restrict__ sdst0, T* __restrict__ sdst1, const int sbase) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const bool two = xp1 != nullptr;
+  T x0[QR_MAXR], x1[QR_MAXR];
 #pragma unroll
   for (int t = 0; t < QR_MAXR; ++t) {
     const int i = k0 + lane + 32 * t;
-    if (i >= rlo && i <= rlast) { if (sdst && i >= sbase) sdst[i - sbase] = x[t]; else xp[i] = x[t]; }
+    x0[t] = (i >= rlo0 && i <= rlast) ? xp0[i] : T(0);
+    x1[t] = (two && i >= rlo1 && i <= rlast) ? xp1[i] : T(0);
   }
+  int roff[QR_MAXR];   // row offsets clamped into the column (x is zero there)
+#pragma unroll
+  for (int t = 0; t < QR_MAXR; ++t) roff[t] = min(lane + 32 * t, LV - 1);
+#pragma unroll 2
+  for (int c = 0; c < QR_PB; ++c) {
+    const T* vc = sV + c * LV;
+    T d0a = T(0), d0b = T(0), d1a = T(0), d1b = T(0);
+#pragma unroll
+    for (int t = 0; t < QR_MAXR; t += 2) {
+      const T va = vc[roff[t]], vb = vc[roff[t + 1]];
+      d0a += va * x0[t]; d0b += vb * x0[t + 1];
+      d1a += va * x1[t]; d1b += vb * x1[t + 1];
+    }
+    ws[c * 33 + lane] = d0a + d0b;
+    ws[(8 + c) * 33 + lane] = d1a + d1b;
+  }
+  __syncwarp();
+  T tot = T(0);
+  {
+    const T* wr = ws + (lane & 15) * 33;
+    T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+#pragma unroll
+    for (int l = 0; l < 32; l += 4) { s0 += wr[l]; s1 += wr[l + 1]; s2 += wr[l + 2]; s3 += wr[l + 3]; }
+    tot = (s0 + s1) + (s2 + s3);   // lanes 0..7: w of column 0, lanes 8..15: w of column 1 (16..31 mirror them)
+  }
+  // z_j = sum_{i <= j} T(i, j) w_i within the lane's group of 8
+  {
+    const int j = lane & 7, grp = lane & 8;
+    T z = T(0);
+#pragma unroll
+    for (int i = 0; i < QR_PB; ++i) {
+      const T wi = __shfl_sync(FULL, tot, grp + i);
+      if (i <= j) z += sT[i * QR_PB + j] * wi;
+    }
+    __syncwarp();
+    if (lane < 16) ws[16 * 33 + lane] = z;
+  }
+  __syncwarp();
+#pragma unroll 2
+  for (int c = 0; c < QR_PB; ++c) {
+    const T* vc = sV + c * LV;
+    const T z0 = ws[16 * 33 + c], z1 = ws[16 * 33 + 8 + c];
+#pragma unroll
+    for (int t = 0; t < QR_MAXR; ++t) {
+      const T vv = vc[roff[t]];
+      x0[t] -= vv * z0;
+      x1[t] -= vv * z1;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < QR_MAXR; ++t) {
+    const int i = k0 + lane + 32 * t;
+    if (i >= rlo0 && i <= rlast) { if (sdst0 && i >= sbase) sdst0[i - sbase] = x0[t]; else xp0[i] = x0[t]; }
+    if (two && i >= rlo1 && i <= rlast) { if (sdst1 && i >= sbase) sdst1[i - sbase] = x1[t]; else xp1[i] = x1[t]; }
+  }
+  __syncwarp();
 }
 
-// panel columns k0 .. k0+pb-1 (rows >= k0) from global memory, factor in shared memory, write back + tau (one CTA)
+#ifdef BA_QR_TICKS
+__device__ long long qr_ftick[8];
+#endif
+// Factor the panel columns k0 .. k0+pb-1 in sP (one CTA): local rows [0, rows_staged) of every column are already
+// there (written by qr_apply_wy); the remaining band rows come from global memory, everything else is zero
+// (rows_staged == 0: whole panel from global memory). Writes the factored panel and tau back, T to sTout and Tg.
+// Thread t owns the local rows t, t + 256, t + 512 of every column.
 template <class T>
-__device__ __forceinline__ void qr_factor_panel(const QRMat<T>& Q, T* __restrict__ sP, T* __restrict__ spart, T* __restrict__ tauv, const int LV,
-                                                const int k0, const int pb, const int rows_staged) {
-  // rows_staged: local rows [0, rows_staged) of every column are already in sP (written by qr_apply_panel); the
-  // remaining band rows (at most pb per column) come from global memory, everything else is zero
+__device__ __noinline__ void qr_factor_panel(const QRMat<T>& Q, T* __restrict__ sP, T* __restrict__ spart, T* __restrict__ sG, T* __restrict__ sTout,
+                                             T* __restrict__ tauv, T* __restrict__ Tg, const int LV, const int k0, const int pb,
+                                             const int rows_staged) {
+  constexpr unsigned FULL = 0xffffffffu;
   constexpr int NW = QR_THREADS / 32;
-  const int n = Q.n, kd = Q.kd;
+  const int n = Q.n, kd = Q.kd, ku = Q.ku;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const T tiny = (sizeof(T) == 8 ? T(2.2250738585072014e-308) : T(1.17549435e-38f));
-  if (rows_staged == 0) {
-    for (int idx0 = 0; idx0 < pb * LV; idx0 += 4 * QR_THREADS) {
-      T tmp[4];
+#ifdef BA_QR_TICKS
+  long long ft_ = clock64();
+#define FTICK(i) { if (threadIdx.x == 0) { const long long t1_ = clock64(); qr_ftick[i] += t1_ - ft_; ft_ = t1_; } __syncwarp(); }
+#else
+#define FTICK(i) {}
+#endif
+  int ru[QR_RPT]; bool rin[QR_RPT];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = idx0 + tid + QR_THREADS * u, c = idx / LV, r = idx - c * LV, i = k0 + r, j = k0 + c;
-        tmp[u] = (idx < pb * LV && i < n && i <= j + kd) ? gq(Q, i, j) : T(0);
+  for (int u = 0; u < QR_RPT; ++u) { const int r = tid + QR_THREADS * u; rin[u] = r < LV; ru[u] = min(r, LV - 1); }
+  // rows not staged yet: local rows [rows_staged, LV) of every column, straight from the band storage
+  {
+    T tmp[QR_PB][QR_RPT];
+#pragma unroll
+    for (int c = 0; c < QR_PB; ++c)
+#pragma unroll
+      for (int u = 0; u < QR_RPT; ++u) {
+        const int r = ru[u], i = k0 + r, j = k0 + c;
+        const bool ld_ = rin[u] && r >= rows_staged && c < pb && i < n && i <= j + kd;
+        tmp[c][u] = ld_ ? Q.G[(size_t)j * Q.ld + (r - c + ku)] : T(0);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { const int idx = idx0 + tid + QR_THREADS * u; if (idx < pb * LV) sP[idx] = tmp[u]; }
-    }
-  } else {
-    const int nrest = LV - rows_staged;  // <= QR_PB local rows per column
-    for (int idx = tid; idx < pb * nrest; idx += QR_THREADS) {
-      const int c = idx / nrest, r = rows_staged + (idx - c * nrest), i = k0 + r, j = k0 + c;
-      sP[c * LV + r] = (i < n && i <= j + kd) ? gq(Q, i, j) : T(0);
-    }
+    for (int c = 0; c < QR_PB; ++c)
+#pragma unroll
+      for (int u = 0; u < QR_RPT; ++u)
+        if (rin[u] && ru[u] >= rows_staged && c < pb) sP[c * LV + ru[u]] = tmp[c][u];
   }
+  if (tid < 64) { sTout[tid] = T(0); sG[tid] = T(0); }
   __syncthreads();
-  T pend[QR_PB + 1];   // thread 0: row-c entries of column c's step, written after the next barrier
+  FTICK(0)
+  T pend[QR_PB];       // thread 0: row-c entries of column c's step, written after the next barrier
   int pend_c = -1;
-  T mytau = T(0);      // thread c keeps tau_c
-  for (int c = 0; c < pb; ++c) {
-    T* v = sP + c * LV;
+  T mytau = T(0);      // thread c: tau_c
+#pragma unroll
+  for (int q = 0; q < QR_PB; ++q) pend[q] = T(0);
+#pragma unroll 1
+  for (int c = 0; c < pb; ++c) {  // rolled, and the function is not inlined: unrolled x 2 call sites the kernel was 266 KB of code
+    const int cLV = c * LV;
     const int rend = min(n - 1, k0 + c + kd) - k0;  // last local row of this column
+    // slot 0: |tail|^2; slots 1 .. pb-1-c: <tail, x_{c+s}> (remaining columns); slots pb-c .. pb-1: <tail, v_i>, i = s-(pb-c)
+    int soff[QR_PB];
+#pragma unroll
+    for (int q = 1; q < QR_PB; ++q) soff[q] = ((q <= pb - 1 - c) ? c + q : q - (pb - c)) * LV;
     T acc[QR_PB];
 #pragma unroll
     for (int q = 0; q < QR_PB; ++q) acc[q] = T(0);
     T vr[QR_RPT];
 #pragma unroll
     for (int u = 0; u < QR_RPT; ++u) {
-      const int r = tid + QR_THREADS * u;
-      const bool ok = r > c && r <= rend;
-      vr[u] = ok ? v[r] : T(0);
+      const bool ok = rin[u] && ru[u] > c && ru[u] <= rend;
+      vr[u] = ok ? sP[cLV + ru[u]] : T(0);
       acc[0] += vr[u] * vr[u];
 #pragma unroll
-      for (int q = 1; q < QR_PB; ++q) if (c + q < pb && ok) acc[q] += vr[u] * sP[(c + q) * LV + r];
+      for (int q = 1; q < QR_PB; ++q) acc[q] += vr[u] * sP[soff[q] + ru[u]];   // slots >= pb read a valid column, never used
     }
-#pragma unroll
-    for (int q = 0; q < QR_PB; ++q) acc[q] = warp_sum(acc[q]);
-    T* part = spart + (c & 1) * NW * (QR_PB + 1);
-    if (lane == 0) {
-#pragma unroll
-      for (int q = 0; q < QR_PB; ++q) part[warp * (QR_PB + 1) + q] = acc[q];
-    }
+    FTICK(1)
+    const T mine = warp_reduce_scatter<T, 8, 3>(acc, lane);  // lane holds slot (lane >> 2) & 7
+    T* part = spart + (c & 1) * 64;
+    if ((lane & 3) == 0) part[warp * 8 + (lane >> 2)] = mine;
     __syncthreads();
+    FTICK(2)
     if (tid == 0 && pend_c >= 0) {  // deferred row writes of the previous column (all its readers are past the barrier)
-      T* pv = sP + pend_c * LV;
-      pv[pend_c] = pend[0];
+      sP[pend_c * LV + pend_c] = pend[0];
 #pragma unroll
       for (int q = 1; q < QR_PB; ++q) if (pend_c + q < pb) sP[(pend_c + q) * LV + pend_c] = pend[q];
     }
+    // every warp: lane s (< 8) sums slot s over the warps, then the 8 totals are broadcast
+    T ssum;
+    {
+      const T* pp = part + (lane & 7);
+      ssum = ((pp[0] + pp[8]) + (pp[16] + pp[24])) + ((pp[32] + pp[40]) + (pp[48] + pp[56]));
+    }
     T tot[QR_PB];
 #pragma unroll
-    for (int q = 0; q < QR_PB; ++q) { T t2 = T(0); for (int w = 0; w < NW; ++w) t2 += part[w * (QR_PB + 1) + q]; tot[q] = t2; }
-    const T c0 = v[c];
+    for (int q = 0; q < QR_PB; ++q) tot[q] = __shfl_sync(FULL, ssum, q);
+    const T c0 = sP[cLV + c];
     T tau = T(0), inv = T(0), beta = c0;
-    if (tot[0] > tiny) {
-      beta = sqrt(c0 * c0 + tot[0]);
-      if (c0 >= T(0)) beta = -beta;
-      inv = T(1) / (c0 - beta);
-      tau = (beta - c0) / beta;
-    }
+    if (tot[0] > tiny) householder_scalars(c0, tot[0], beta, inv, tau);
     if (tid == c) mytau = tau;
-    // t_q = tau * (x_q(c) + inv * <tail, x_q>): x_q -= t_q * v_normalised, v_normalised = inv * tail below row c, 1 at row c
+    FTICK(3)
+    // t_q = tau * (x_q(c) + inv * <tail, x_q>): x_q -= t_q * v_normalised (inv * tail below row c, 1 at row c)
     T tq[QR_PB];
 #pragma unroll
-    for (int q = 1; q < QR_PB; ++q) tq[q] = (c + q < pb) ? tau * (sP[(c + q) * LV + c] + inv * tot[q]) : T(0);
+    for (int q = 1; q < QR_PB; ++q) tq[q] = (q <= pb - 1 - c) ? tau * (sP[soff[q] + c] + inv * tot[q]) : T(0);
     if (tid == 0) {
       pend_c = c; pend[0] = beta;
 #pragma unroll
-      for (int q = 1; q < QR_PB; ++q) if (c + q < pb) pend[q] = sP[(c + q) * LV + c] - tq[q];
+      for (int q = 1; q < QR_PB; ++q) if (q <= pb - 1 - c) pend[q] = sP[soff[q] + c] - tq[q];
     }
+    // g_i = <v_i, v_c> = v_i(c) + inv * <tail, v_i> for the previous reflectors (T is formed after the loop)
+    if (warp == NW - 1 && lane >= 1 && lane < QR_PB && lane >= pb - c) sG[c * QR_PB + (lane - (pb - c))] = sP[(lane - (pb - c)) * LV + c] + inv * ssum;
+    FTICK(4)
     if (tau != T(0)) {
 #pragma unroll
       for (int u = 0; u < QR_RPT; ++u) {
-        const int r = tid + QR_THREADS * u;
-        if (r > c && r <= rend) {
+        if (rin[u] && ru[u] > c && ru[u] <= rend) {
           const T vn = vr[u] * inv;
-          v[r] = vn;
+          sP[cLV + ru[u]] = vn;
 #pragma unroll
-          for (int q = 1; q < QR_PB; ++q) if (c + q < pb) sP[(c + q) * LV + r] -= tq[q] * vn;
+          for (int q = 1; q < QR_PB; ++q) if (q <= pb - 1 - c) sP[soff[q] + ru[u]] -= tq[q] * vn;
         }
       }
+    } else {
+      // H = I: the stored tail must read as zero for the WY form
+#pragma unroll
+      for (int u = 0; u < QR_RPT; ++u) if (rin[u] && ru[u] > c && ru[u] <= rend) sP[cLV + ru[u]] = T(0);
     }
+    FTICK(5)
     // no barrier here: the next column's first pass touches only rows this thread owns; the row-c entries read
     // above are rewritten by thread 0 after the next barrier
   }
   __syncthreads();
   if (tid == 0 && pend_c >= 0) {
-    T* pv = sP + pend_c * LV;
-    pv[pend_c] = pend[0];
+    sP[pend_c * LV + pend_c] = pend[0];
 #pragma unroll
     for (int q = 1; q < QR_PB; ++q) if (pend_c + q < pb) sP[(pend_c + q) * LV + pend_c] = pend[q];
   }
   if (tid < pb) tauv[k0 + tid] = mytau;
-  __syncthreads();
-  for (int idx = tid; idx < pb * LV; idx += QR_THREADS) {
-    const int c = idx / LV, r = idx - c * LV, i = k0 + r, j = k0 + c;
-    if (i < n && i <= j + kd) gq(Q, i, j) = sP[idx];
+  // T (dlarft, forward columnwise): T(c, c) = tau_c, T(0:c, c) = -tau_c T(0:c, 0:c) g(0:c, c); thread i owns row i
+  if (tid < QR_PB) {
+    T trow[QR_PB];
+#pragma unroll
+    for (int c = 0; c < QR_PB; ++c) {
+      const T tc = __shfl_sync(0xffu, mytau, c);
+      T sacc = T(0);
+#pragma unroll
+      for (int m = 0; m < QR_PB; ++m) if (m < c) sacc += ((m >= tid) ? trow[m] : T(0)) * sG[c * QR_PB + m];
+      trow[c] = (tid == c) ? tc : ((tid < c) ? -tc * sacc : T(0));
+    }
+#pragma unroll
+    for (int q = 0; q < QR_PB; ++q) { sTout[tid * QR_PB + q] = trow[q]; Tg[tid * QR_PB + q] = trow[q]; }
   }
+  __syncthreads();
+  // write-back: every band row of the panel columns (rows >= k0)
+#pragma unroll
+  for (int c = 0; c < QR_PB; ++c)
+#pragma unroll
+    for (int u = 0; u < QR_RPT; ++u) {
+      const int r = ru[u], i = k0 + r, j = k0 + c;
+      if (rin[u] && c < pb && i < n && i <= j + kd) Q.G[(size_t)j * Q.ld + (r - c + ku)] = sP[c * LV + r];
+    }
+  FTICK(6)
+#undef FTICK
 }
 
 template <class T>
-__global__ void __launch_bounds__(QR_THREADS) k_band_qr_reg(QRMat<T> Q, T* __restrict__ tauv, T* __restrict__ rhs, long long* __restrict__ dbg) {
+__global__ void __launch_bounds__(QR_THREADS) k_band_qr_reg(QRMat<T> Q, T* __restrict__ tauv, T* __restrict__ rhs, T* __restrict__ Tg2,
+                                                            long long* __restrict__ dbg) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char qr_smem_raw[];
@@ -321,63 +464,76 @@ __global__ void __launch_bounds__(QR_THREADS) k_band_qr_reg(QRMat<T> Q, T* __res
   const int LV = kd + QR_PB;                       // rows k0 .. k0+LV-1 cover every reflector of a panel
   T* sV = reinterpret_cast<T*>(qr_smem_raw);       // [QR_PB][LV] reflector vectors of the current panel
   T* sP = sV + QR_PB * LV;                         // [QR_PB][LV] panel being factored (CTA 0)
-  T* stau = sV + 2 * QR_PB * LV;                   // [QR_PB]
-  T* spart = stau + QR_PB;                         // [2][NW][QR_PB + 1]
+  T* sT = sV + 2 * QR_PB * LV;                     // [64] T of the current panel
+  T* sTn = sT + 64;                                // [64] T of the panel being factored (CTA 0)
+  T* spart = sTn + 64;                             // [2][8][8]
+  T* sG = spart + 128;                             // [64]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  T* ws = sG + 64 + warp * QR_WS;                  // per-warp scratch of qr_apply_wy
   const bool panel_cta = blockIdx.x == 0;
   const int nupd = max(1, (int)gridDim.x - 1);     // CTAs that update trailing columns (all of them when the grid is one CTA)
   const int ucta = (gridDim.x > 1) ? (int)blockIdx.x - 1 : 0;
-  if (panel_cta) qr_factor_panel<T>(Q, sP, spart, tauv, LV, 0, min(QR_PB, n), 0);
+  if (panel_cta) qr_factor_panel<T>(Q, sP, spart, sG, sTn, tauv, Tg2, LV, 0, min(QR_PB, n), 0);
   __threadfence();
   grid.sync();
-  for (int k0 = 0; k0 < n; k0 += QR_PB) {
+  int par = 0;  // parity of the current panel: its T sits in Tg2 + 64 * par
+  for (int k0 = 0; k0 < n; k0 += QR_PB, par ^= 1) {
     const int pb = min(QR_PB, n - k0);
     QTICK(0)
     if (panel_cta) {
-      // the panel CTA factored this panel in sP: it becomes sV by swapping the buffers (entries on and above the
-      // diagonal are masked instead of re-reading the panel from global memory)
+      // the panel CTA factored this panel in sP / sTn: they become sV / sT by swapping the buffers
       T* tswap = sV; sV = sP; sP = tswap;
-      for (int idx = tid; idx < pb * (QR_PB + 1); idx += QR_THREADS) { const int c = idx / (QR_PB + 1), r = idx - c * (QR_PB + 1); if (r <= c) sV[c * LV + r] = T(0); }
+      tswap = sT; sT = sTn; sTn = tswap;
+      for (int idx = tid; idx < QR_PB * (QR_PB + 1); idx += QR_THREADS) {
+        const int c = idx / (QR_PB + 1), r = idx - c * (QR_PB + 1);
+        if (r <= c) sV[c * LV + r] = (r == c && c < pb) ? T(1) : T(0);
+      }
+      if (pb < QR_PB) for (int idx = tid; idx < (QR_PB - pb) * LV; idx += QR_THREADS) sV[pb * LV + idx] = T(0);
     } else {
-      // reflector vectors of this panel -> shared memory (v(col) = 1 implicit; sV[c][r] valid for r > c), loads batched
-      for (int idx0 = 0; idx0 < pb * LV; idx0 += 4 * QR_THREADS) {
-        T tmp[4];
+      // reflector vectors of this panel -> shared memory (unit diagonal, zeros above): 24 independent loads per thread
+      T tmp[QR_PB][QR_RPT];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = idx0 + tid + QR_THREADS * u, c = idx / LV, r = idx - c * LV, i = k0 + r, j = k0 + c;
-          tmp[u] = (idx < pb * LV && r > c && i < n && i <= j + kd) ? gq(Q, i, j) : T(0);
+      for (int c = 0; c < QR_PB; ++c)
+#pragma unroll
+        for (int u = 0; u < QR_RPT; ++u) {
+          const int r = tid + QR_THREADS * u, i = k0 + r, j = k0 + c;
+          const bool ld_ = r < LV && c < pb && r > c && i < n && i <= j + kd;
+          tmp[c][u] = ld_ ? Q.G[(size_t)j * Q.ld + (r - c + ku)] : ((r == c && c < pb) ? T(1) : T(0));
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int idx = idx0 + tid + QR_THREADS * u; if (idx < pb * LV) sV[idx] = tmp[u]; }
-      }
+      for (int c = 0; c < QR_PB; ++c)
+#pragma unroll
+        for (int u = 0; u < QR_RPT; ++u) { const int r = tid + QR_THREADS * u; if (r < LV) sV[c * LV + r] = tmp[c][u]; }
+      if (tid < 64) sT[tid] = Tg2[64 * par + tid];
     }
-    if (tid < pb) stau[tid] = tauv[k0 + tid];
     __syncthreads();
     QTICK(1)
     const int jlast = min(n - 1, k0 + pb - 1 + ku);
     const int rlast = min(n - 1, k0 + pb - 1 + kd);  // last row any reflector of the panel touches
     const int k1 = k0 + pb, pb1 = min(QR_PB, n - k1);  // next panel (pb1 <= 0: none)
     if (panel_cta) {
-      // next-panel columns: rows [k1, rlast] land in sP (local rows [0, rlast - k1]); zero the staged part first for
-      // the rows a column's band does not reach
+      // next-panel columns, one per warp: rows [k1, rlast] land in sP (local rows [0, rlast - k1])
       const int staged = max(0, rlast - k1 + 1);
       for (int w = warp; w < pb1; w += NW) {
-        const int j = k1 + w;   // j <= jlast always (pb1 <= QR_PB <= ku)
-        qr_apply_panel<T>(Q, sV, stau, LV, k0, pb, j, Q.G + (size_t)j * Q.ld + (ku - j), max(k0, j - ku), rlast, false, lane, sP + w * LV, k1);
+        const int j0 = k1 + w;   // j <= jlast always (pb1 <= QR_PB <= ku)
+        qr_apply_wy<T>(sV, sT, ws, LV, k0, rlast, Q.G + (size_t)j0 * Q.ld + (ku - j0), max(k0, j0 - ku), nullptr, 0, lane, sP + w * LV, nullptr, k1);
       }
       __syncthreads();
       QTICK(2)
-      if (pb1 > 0) qr_factor_panel<T>(Q, sP, spart, tauv, LV, k1, pb1, staged);
+      if (pb1 > 0) qr_factor_panel<T>(Q, sP, spart, sG, sTn, tauv, Tg2 + 64 * (par ^ 1), LV, k1, pb1, staged);
       QTICK(3)
     }
     if (!panel_cta || gridDim.x == 1) {
       const int jfirst = k1 + max(pb1, 0);
-      const int ntrail = jlast - jfirst + 1;  // may be <= 0
-      for (int w = ucta * NW + warp; w < max(ntrail, 0) + 1; w += nupd * NW) {
-        const bool is_rhs = (w == max(ntrail, 0));
-        const int j = is_rhs ? n : (jfirst + w);
-        T* xp = is_rhs ? rhs : (Q.G + (size_t)j * Q.ld + (ku - j));  // x(r) = xp[r]
-        qr_apply_panel<T>(Q, sV, stau, LV, k0, pb, j, xp, is_rhs ? k0 : max(k0, j - ku), rlast, is_rhs, lane);
+      const int ntrail = max(0, jlast - jfirst + 1);  // trailing columns; item ntrail is the right-hand side
+      const int nitems = ntrail + 1, ntask = (nitems + 1) / 2;
+      for (int w = ucta * NW + warp; w < ntask; w += nupd * NW) {
+        const int it0 = 2 * w, it1 = 2 * w + 1;
+        const bool rhs0 = it0 == ntrail, has1 = it1 < nitems, rhs1 = it1 == ntrail;
+        const int j0 = jfirst + it0, j1 = jfirst + it1;
+        T* xp0 = rhs0 ? rhs : (Q.G + (size_t)j0 * Q.ld + (ku - j0));
+        T* xp1 = !has1 ? nullptr : (rhs1 ? rhs : (Q.G + (size_t)j1 * Q.ld + (ku - j1)));
+        qr_apply_wy<T>(sV, sT, ws, LV, k0, rlast, xp0, rhs0 ? k0 : max(k0, j0 - ku), xp1, rhs1 ? k0 : max(k0, j1 - ku), lane, nullptr, nullptr, 0);
       }
     }
     QTICK(4)
@@ -386,7 +542,7 @@ __global__ void __launch_bounds__(QR_THREADS) k_band_qr_reg(QRMat<T> Q, T* __res
     QTICK(5)
   }
 #ifdef BA_QR_TICKS
-  if (dbg && tid == 0 && blockIdx.x <= 1) for (int i = 0; i < 8; ++i) dbg[8 * blockIdx.x + i] = tk_[i];
+  if (dbg && tid == 0 && blockIdx.x == 0) for (int i = 0; i < 8; ++i) { dbg[i] = tk_[i]; dbg[8 + i] = qr_ftick[i]; qr_ftick[i] = 0; }
 #endif
 #undef QTICK
 }

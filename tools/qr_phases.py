@@ -8,7 +8,9 @@ for _ in range(2):
     s.compute(1e-12 * cn2); s.solve_try(); s.reject()
 c = s.debug_counters()
 names = ["loop top", "reflectors -> smem + barrier", "apply panel to next-panel columns", "factor next panel", "trailing update", "fence + grid barrier", "-", "-"]
+fnames = ["panel rows -> smem + barrier", "column pass 1 (dots)", "warp reduce + block barrier", "totals + beta/tau", "t_q + T column", "column pass 2 (update)", "final barrier + write-back", "-"]
 npanel = (9 * p.N + 7) // 8
-for who, off in (("panel CTA", 0), ("update CTA", 8)):
-    for n, v in zip(names, c[off:off + 8]):
-        print(f"{who:10s} {n:36s} {v:12d} cycles = {v/1.965e3/npanel:7.2f} us/panel")
+for n, v in zip(names, c[:8]):
+    print(f"panel CTA  {n:36s} {v:12d} cycles = {v/1.965e3/npanel:7.2f} us/panel")
+for n, v in zip(fnames, c[8:]):
+    print(f"  factor:  {n:36s} {v:12d} cycles = {v/1.965e3/npanel:7.2f} us/panel")
