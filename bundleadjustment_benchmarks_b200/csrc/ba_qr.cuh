@@ -162,8 +162,9 @@ static_assert(QR_PB == 8 && QR_THREADS == 256, "the reductions of the panel kern
 constexpr int QR_WS = 16 * 33 + 16;   // per-warp scratch of qr_apply_wy: partial dots [16][33] + z [16]
 template <class T>
 struct QrSmem {
-  // dynamic layout: sV[QR_PB][LV] | sP[QR_PB][LV] | sT[64] | sTn[64] | spart[2][64] | sG[64] | ws[8][QR_WS]
-  static size_t bytes(int kd) { return ((size_t)2 * QR_PB * (kd + QR_PB) + 5 * 64 + (QR_THREADS / 32) * QR_WS) * sizeof(T); }
+  // dynamic layout: sV[QR_PB][LV] | sP[QR_PB][LV] | sT[64] | sTn[64] | spart[2][64] | sRow[2][8] | sG[64] | ws[8][QR_WS]
+  // (the panel CTA's qr_apply_cta uses the ws area as [8][32] partial sums + [64] W / Z)
+  static size_t bytes(int kd) { return ((size_t)2 * QR_PB * (kd + QR_PB) + 5 * 64 + 16 + (QR_THREADS / 32) * QR_WS) * sizeof(T); }
 };
 
 // Reduce-scatter over the warp followed by a butterfly on the surviving entry: on return every lane holds the warp
@@ -290,10 +291,98 @@ __device__ __noinline__ void qr_apply_wy(const T* __restrict__ sV, const T* __re
 #ifdef BA_QR_TICKS
 __device__ long long qr_ftick[8];
 #endif
-// Factor the panel columns k0 .. k0+pb-1 in sP (one CTA): local rows [0, rows_staged) of every column are already
-// there (written by qr_apply_wy); the remaining band rows come from global memory, everything else is zero
-// (rows_staged == 0: whole panel from global memory). Writes the factored panel and tau back, T to sTout and Tg.
-// Thread t owns the local rows t, t + 256, t + 512 of every column.
+// ---- panel CTA, register-resident. Thread t owns the local rows t, t+256, t+512 of all 8 columns (24 scalars).
+// The panel factorisation in shared memory was bound by shared-memory bandwidth (every column step re-read and
+// re-wrote the remaining columns: 480 KB per panel; r1 v6b: 7.5 us of passes per panel), and so was the
+// warp-per-column application on this CTA (every warp read all of V twice: 570 KB).
+
+// x -= V (T^T (V^T x)) for the next panel's columns (global columns k1 .. k1+pb1-1), the whole CTA at once:
+// rows relative to k0 in registers, V read once from shared memory, the 64 dot products reduced in two rounds of 32.
+// Rows [k0, k1) go back to global memory (final rows of R), rows >= k1 to sP in the factorisation's layout.
+template <class T>
+__device__ __noinline__ void qr_apply_cta(const QRMat<T>& Q, const T* __restrict__ sV, const T* __restrict__ sT, T* __restrict__ sW, T* __restrict__ sP,
+                                          const int LV, const int k0, const int k1, const int pb1, const int rlast) {
+  constexpr int NW = QR_THREADS / 32;
+  const int n = Q.n, ku = Q.ku;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int ru[QR_RPT]; bool rin[QR_RPT];
+#pragma unroll
+  for (int u = 0; u < QR_RPT; ++u) { const int r = tid + QR_THREADS * u; rin[u] = r < LV; ru[u] = min(r, LV - 1); }
+  T x[QR_PB][QR_RPT];
+#pragma unroll
+  for (int q = 0; q < QR_PB; ++q)
+#pragma unroll
+    for (int u = 0; u < QR_RPT; ++u) {
+      const int i = k0 + ru[u], j = k1 + q;
+      const bool ok = rin[u] && q < pb1 && i <= rlast && i >= j - ku && i < n;
+      x[q][u] = ok ? Q.G[(size_t)j * Q.ld + (i - j + ku)] : T(0);
+    }
+  T* part = sW;            // [NW][32]
+  T* sWt = sW + NW * 32;   // [64] W, then Z
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    T w[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) w[e] = T(0);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = 4 * half + cc;
+#pragma unroll
+      for (int u = 0; u < QR_RPT; ++u) {
+        const T vv = rin[u] ? sV[c * LV + ru[u]] : T(0);
+#pragma unroll
+        for (int q = 0; q < QR_PB; ++q) w[cc * 8 + q] += vv * x[q][u];
+      }
+    }
+    const T mine = warp_reduce_scatter<T, 32, 5>(w, lane);  // lane holds entry lane
+    part[warp * 32 + lane] = mine;
+    __syncthreads();
+    if (tid < 32) {
+      T sacc = T(0);
+#pragma unroll
+      for (int w2 = 0; w2 < NW; ++w2) sacc += part[w2 * 32 + tid];
+      sWt[32 * half + tid] = sacc;   // W(c, q) at c * 8 + q
+    }
+    __syncthreads();
+  }
+  // Z = T^T W: Z(j, q) = sum_{i <= j} T(i, j) W(i, q)
+  T zreg = T(0);
+  if (tid < 64) {
+    const int j = tid >> 3, q = tid & 7;
+#pragma unroll
+    for (int i = 0; i < QR_PB; ++i) if (i <= j) zreg += sT[i * QR_PB + j] * sWt[i * 8 + q];
+  }
+  __syncthreads();
+  if (tid < 64) sWt[tid] = zreg;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < QR_PB; ++c) {
+    T z[QR_PB];
+#pragma unroll
+    for (int q = 0; q < QR_PB; ++q) z[q] = sWt[c * 8 + q];
+#pragma unroll
+    for (int u = 0; u < QR_RPT; ++u) {
+      const T vv = rin[u] ? sV[c * LV + ru[u]] : T(0);
+#pragma unroll
+      for (int q = 0; q < QR_PB; ++q) x[q][u] -= vv * z[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < QR_PB; ++q)
+#pragma unroll
+    for (int u = 0; u < QR_RPT; ++u) {
+      const int i = k0 + ru[u], j = k1 + q;
+      if (rin[u] && q < pb1 && i <= rlast && i >= j - ku && i < n) {
+        if (i >= k1) sP[q * LV + (i - k1)] = x[q][u]; else Q.G[(size_t)j * Q.ld + (i - j + ku)] = x[q][u];
+      }
+    }
+}
+
+// Factor the panel columns k0 .. k0+pb-1 (one CTA), panel in registers: local rows [0, rows_staged) of every column
+// come from sP (written by qr_apply_cta), the remaining band rows from global memory (rows_staged == 0: everything
+// from global memory). One block barrier per column: a single pass accumulates |tail|^2, the dot products with the
+// remaining columns and with the previous reflectors (for T); every thread then derives beta / tau redundantly and
+// updates its rows. Leaves the factored panel in sP (it becomes sV), in global memory, tau in tauv, T in sTout / Tg.
 template <class T>
 __device__ __noinline__ void qr_factor_panel(const QRMat<T>& Q, T* __restrict__ sP, T* __restrict__ spart, T* __restrict__ sG, T* __restrict__ sTout,
                                              T* __restrict__ tauv, T* __restrict__ Tg, const int LV, const int k0, const int pb,
@@ -309,116 +398,93 @@ __device__ __noinline__ void qr_factor_panel(const QRMat<T>& Q, T* __restrict__ 
 #else
 #define FTICK(i) {}
 #endif
+  T* sRow = spart + 128;   // [2][8] row c of every column, published by the thread that owns it
   int ru[QR_RPT]; bool rin[QR_RPT];
 #pragma unroll
   for (int u = 0; u < QR_RPT; ++u) { const int r = tid + QR_THREADS * u; rin[u] = r < LV; ru[u] = min(r, LV - 1); }
-  // rows not staged yet: local rows [rows_staged, LV) of every column, straight from the band storage
-  {
-    T tmp[QR_PB][QR_RPT];
+  T p[QR_PB][QR_RPT];
 #pragma unroll
-    for (int c = 0; c < QR_PB; ++c)
-#pragma unroll
-      for (int u = 0; u < QR_RPT; ++u) {
-        const int r = ru[u], i = k0 + r, j = k0 + c;
-        const bool ld_ = rin[u] && r >= rows_staged && c < pb && i < n && i <= j + kd;
-        tmp[c][u] = ld_ ? Q.G[(size_t)j * Q.ld + (r - c + ku)] : T(0);
-      }
-#pragma unroll
-    for (int c = 0; c < QR_PB; ++c)
-#pragma unroll
-      for (int u = 0; u < QR_RPT; ++u)
-        if (rin[u] && ru[u] >= rows_staged && c < pb) sP[c * LV + ru[u]] = tmp[c][u];
-  }
-  if (tid < 64) { sTout[tid] = T(0); sG[tid] = T(0); }
-  __syncthreads();
-  FTICK(0)
-  T pend[QR_PB];       // thread 0: row-c entries of column c's step, written after the next barrier
-  int pend_c = -1;
-  T mytau = T(0);      // thread c: tau_c
-#pragma unroll
-  for (int q = 0; q < QR_PB; ++q) pend[q] = T(0);
-#pragma unroll 1
-  for (int c = 0; c < pb; ++c) {  // rolled, and the function is not inlined: unrolled x 2 call sites the kernel was 266 KB of code
-    const int cLV = c * LV;
-    const int rend = min(n - 1, k0 + c + kd) - k0;  // last local row of this column
-    // slot 0: |tail|^2; slots 1 .. pb-1-c: <tail, x_{c+s}> (remaining columns); slots pb-c .. pb-1: <tail, v_i>, i = s-(pb-c)
-    int soff[QR_PB];
-#pragma unroll
-    for (int q = 1; q < QR_PB; ++q) soff[q] = ((q <= pb - 1 - c) ? c + q : q - (pb - c)) * LV;
-    T acc[QR_PB];
-#pragma unroll
-    for (int q = 0; q < QR_PB; ++q) acc[q] = T(0);
-    T vr[QR_RPT];
+  for (int c = 0; c < QR_PB; ++c)
 #pragma unroll
     for (int u = 0; u < QR_RPT; ++u) {
-      const bool ok = rin[u] && ru[u] > c && ru[u] <= rend;
-      vr[u] = ok ? sP[cLV + ru[u]] : T(0);
-      acc[0] += vr[u] * vr[u];
-#pragma unroll
-      for (int q = 1; q < QR_PB; ++q) acc[q] += vr[u] * sP[soff[q] + ru[u]];   // slots >= pb read a valid column, never used
+      const int r = ru[u], i = k0 + r, j = k0 + c;
+      const bool inband = rin[u] && c < pb && i < n && i <= j + kd;
+      T v = T(0);
+      if (inband) v = (r < rows_staged) ? sP[c * LV + r] : Q.G[(size_t)j * Q.ld + (r - c + ku)];
+      p[c][u] = v;
     }
-    FTICK(1)
-    const T mine = warp_reduce_scatter<T, 8, 3>(acc, lane);  // lane holds slot (lane >> 2) & 7
-    T* part = spart + (c & 1) * 64;
-    if ((lane & 3) == 0) part[warp * 8 + (lane >> 2)] = mine;
-    __syncthreads();
-    FTICK(2)
-    if (tid == 0 && pend_c >= 0) {  // deferred row writes of the previous column (all its readers are past the barrier)
-      sP[pend_c * LV + pend_c] = pend[0];
+  if (tid < 64) sG[tid] = T(0);
+  T mytau = T(0);      // thread c: tau_c
+  FTICK(0)
 #pragma unroll
-      for (int q = 1; q < QR_PB; ++q) if (pend_c + q < pb) sP[(pend_c + q) * LV + pend_c] = pend[q];
-    }
-    // every warp: lane s (< 8) sums slot s over the warps, then the 8 totals are broadcast
-    T ssum;
-    {
-      const T* pp = part + (lane & 7);
-      ssum = ((pp[0] + pp[8]) + (pp[16] + pp[24])) + ((pp[32] + pp[40]) + (pp[48] + pp[56]));
-    }
-    T tot[QR_PB];
+  for (int c = 0; c < QR_PB; ++c) {
+    if (c < pb) {
+      const int rend = min(n - 1, k0 + c + kd) - k0;  // last local row of this column
+      if (tid == c) {
 #pragma unroll
-    for (int q = 0; q < QR_PB; ++q) tot[q] = __shfl_sync(FULL, ssum, q);
-    const T c0 = sP[cLV + c];
-    T tau = T(0), inv = T(0), beta = c0;
-    if (tot[0] > tiny) householder_scalars(c0, tot[0], beta, inv, tau);
-    if (tid == c) mytau = tau;
-    FTICK(3)
-    // t_q = tau * (x_q(c) + inv * <tail, x_q>): x_q -= t_q * v_normalised (inv * tail below row c, 1 at row c)
-    T tq[QR_PB];
+        for (int q = 0; q < QR_PB; ++q) sRow[(c & 1) * 8 + q] = p[q][0];
+      }
+      // slot 0: |tail|^2; slots 1 .. 7-c: <tail, x_{c+s}>; slots 8-c .. 7: <tail, v_i>, i = s-(8-c)
+      T acc[QR_PB], vr[QR_RPT];
 #pragma unroll
-    for (int q = 1; q < QR_PB; ++q) tq[q] = (q <= pb - 1 - c) ? tau * (sP[soff[q] + c] + inv * tot[q]) : T(0);
-    if (tid == 0) {
-      pend_c = c; pend[0] = beta;
+      for (int q = 0; q < QR_PB; ++q) acc[q] = T(0);
 #pragma unroll
-      for (int q = 1; q < QR_PB; ++q) if (q <= pb - 1 - c) pend[q] = sP[soff[q] + c] - tq[q];
-    }
-    // g_i = <v_i, v_c> = v_i(c) + inv * <tail, v_i> for the previous reflectors (T is formed after the loop)
-    if (warp == NW - 1 && lane >= 1 && lane < QR_PB && lane >= pb - c) sG[c * QR_PB + (lane - (pb - c))] = sP[(lane - (pb - c)) * LV + c] + inv * ssum;
-    FTICK(4)
-    if (tau != T(0)) {
+      for (int u = 0; u < QR_RPT; ++u) {
+        const bool ok = rin[u] && ru[u] > c && ru[u] <= rend;
+        vr[u] = ok ? p[c][u] : T(0);
+        acc[0] += vr[u] * vr[u];
+#pragma unroll
+        for (int q = 1; q < QR_PB; ++q) acc[q] += vr[u] * p[(q <= 7 - c) ? c + q : q - (8 - c)][u];
+      }
+      FTICK(1)
+      const T mine = warp_reduce_scatter<T, 8, 3>(acc, lane);  // lane holds slot (lane >> 2) & 7
+      T* part = spart + (c & 1) * 64;
+      if ((lane & 3) == 0) part[warp * 8 + (lane >> 2)] = mine;
+      __syncthreads();
+      FTICK(2)
+      T ssum;
+      {
+        const T* pp = part + (lane & 7);
+        ssum = ((pp[0] + pp[8]) + (pp[16] + pp[24])) + ((pp[32] + pp[40]) + (pp[48] + pp[56]));
+      }
+      T tot[QR_PB], xrow[QR_PB];
+#pragma unroll
+      for (int q = 0; q < QR_PB; ++q) { tot[q] = __shfl_sync(FULL, ssum, q); xrow[q] = sRow[(c & 1) * 8 + q]; }
+      const T c0 = xrow[c];
+      T tau = T(0), inv = T(0), beta = c0;
+      if (tot[0] > tiny) householder_scalars(c0, tot[0], beta, inv, tau);
+      if (tid == c) mytau = tau;
+      FTICK(3)
+      // t_q = tau * (x_q(c) + inv * <tail, x_q>): x_q -= t_q * v_normalised (inv * tail below row c, 1 at row c)
+      T tq[QR_PB];
+#pragma unroll
+      for (int q = 0; q < QR_PB; ++q) tq[q] = (q > c) ? tau * (xrow[q] + inv * tot[(q > c) ? q - c : 0]) : T(0);
+      // g_i = <v_i, v_c> = v_i(c) + inv * <tail, v_i> for the previous reflectors (T is formed after the loop)
+      if (c > 0 && warp == NW - 1 && lane >= 8 - c && lane < 8) {
+        T xr = T(0);
+#pragma unroll
+        for (int i = 0; i < QR_PB; ++i) if (i == lane - (8 - c)) xr = xrow[i];
+        sG[c * QR_PB + (lane - (8 - c))] = xr + inv * ssum;
+      }
+      FTICK(4)
 #pragma unroll
       for (int u = 0; u < QR_RPT; ++u) {
         if (rin[u] && ru[u] > c && ru[u] <= rend) {
-          const T vn = vr[u] * inv;
-          sP[cLV + ru[u]] = vn;
+          const T vn = vr[u] * inv;   // tau == 0: inv == 0, the stored tail reads as zero (H = I)
+          p[c][u] = vn;
 #pragma unroll
-          for (int q = 1; q < QR_PB; ++q) if (q <= pb - 1 - c) sP[soff[q] + ru[u]] -= tq[q] * vn;
+          for (int q = 0; q < QR_PB; ++q) if (q > c) p[q][u] -= tq[q] * vn;
         }
       }
-    } else {
-      // H = I: the stored tail must read as zero for the WY form
+      if (tid == c) {   // row c of the remaining columns, and the diagonal
+        p[c][0] = beta;
 #pragma unroll
-      for (int u = 0; u < QR_RPT; ++u) if (rin[u] && ru[u] > c && ru[u] <= rend) sP[cLV + ru[u]] = T(0);
+        for (int q = 0; q < QR_PB; ++q) if (q > c) p[q][0] -= tq[q];
+      }
+      FTICK(5)
     }
-    FTICK(5)
-    // no barrier here: the next column's first pass touches only rows this thread owns; the row-c entries read
-    // above are rewritten by thread 0 after the next barrier
   }
   __syncthreads();
-  if (tid == 0 && pend_c >= 0) {
-    sP[pend_c * LV + pend_c] = pend[0];
-#pragma unroll
-    for (int q = 1; q < QR_PB; ++q) if (pend_c + q < pb) sP[(pend_c + q) * LV + pend_c] = pend[q];
-  }
   if (tid < pb) tauv[k0 + tid] = mytau;
   // T (dlarft, forward columnwise): T(c, c) = tau_c, T(0:c, c) = -tau_c T(0:c, 0:c) g(0:c, c); thread i owns row i
   if (tid < QR_PB) {
@@ -434,14 +500,14 @@ __device__ __noinline__ void qr_factor_panel(const QRMat<T>& Q, T* __restrict__ 
 #pragma unroll
     for (int q = 0; q < QR_PB; ++q) { sTout[tid * QR_PB + q] = trow[q]; Tg[tid * QR_PB + q] = trow[q]; }
   }
-  __syncthreads();
-  // write-back: every band row of the panel columns (rows >= k0)
+  // the factored panel: to sP (next iteration's sV) and to the band storage
 #pragma unroll
   for (int c = 0; c < QR_PB; ++c)
 #pragma unroll
     for (int u = 0; u < QR_RPT; ++u) {
       const int r = ru[u], i = k0 + r, j = k0 + c;
-      if (rin[u] && c < pb && i < n && i <= j + kd) Q.G[(size_t)j * Q.ld + (r - c + ku)] = sP[c * LV + r];
+      if (rin[u]) sP[c * LV + r] = p[c][u];
+      if (rin[u] && c < pb && i < n && i <= j + kd) Q.G[(size_t)j * Q.ld + (r - c + ku)] = p[c][u];
     }
   FTICK(6)
 #undef FTICK
@@ -467,7 +533,7 @@ __global__ void __launch_bounds__(QR_THREADS) k_band_qr_reg(QRMat<T> Q, T* __res
   T* sT = sV + 2 * QR_PB * LV;                     // [64] T of the current panel
   T* sTn = sT + 64;                                // [64] T of the panel being factored (CTA 0)
   T* spart = sTn + 64;                             // [2][8][8]
-  T* sG = spart + 128;                             // [64]
+  T* sG = spart + 128 + 16;                        // [64] (spart is followed by sRow[2][8])
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   T* ws = sG + 64 + warp * QR_WS;                  // per-warp scratch of qr_apply_wy
   const bool panel_cta = blockIdx.x == 0;
@@ -512,12 +578,9 @@ __global__ void __launch_bounds__(QR_THREADS) k_band_qr_reg(QRMat<T> Q, T* __res
     const int rlast = min(n - 1, k0 + pb - 1 + kd);  // last row any reflector of the panel touches
     const int k1 = k0 + pb, pb1 = min(QR_PB, n - k1);  // next panel (pb1 <= 0: none)
     if (panel_cta) {
-      // next-panel columns, one per warp: rows [k1, rlast] land in sP (local rows [0, rlast - k1])
+      // next-panel columns, the whole CTA at once: rows [k1, rlast] land in sP (local rows [0, rlast - k1])
       const int staged = max(0, rlast - k1 + 1);
-      for (int w = warp; w < pb1; w += NW) {
-        const int j0 = k1 + w;   // j <= jlast always (pb1 <= QR_PB <= ku)
-        qr_apply_wy<T>(sV, sT, ws, LV, k0, rlast, Q.G + (size_t)j0 * Q.ld + (ku - j0), max(k0, j0 - ku), nullptr, 0, lane, sP + w * LV, nullptr, k1);
-      }
+      if (pb1 > 0) qr_apply_cta<T>(Q, sV, sT, sG + 64, sP, LV, k0, k1, pb1, rlast);
       __syncthreads();
       QTICK(2)
       if (pb1 > 0) qr_factor_panel<T>(Q, sP, spart, sG, sTn, tauv, Tg2 + 64 * (par ^ 1), LV, k1, pb1, staged);
