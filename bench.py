@@ -336,7 +336,7 @@ def run_ours(args):
     roofline["hbm_peak"] = {"value": peak, "unit": "GB/s", "source": peak_src}
 
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only (the scaling runs carry null)
         ms, desc = oracle_time_model(full, args.variant, budget_s=20.0)
         cpu_baseline = {"value": ms, "unit": "ms", "cores": 1, "kind": "port", "sample": desc,
                         "host_cores_available": os.cpu_count()}
