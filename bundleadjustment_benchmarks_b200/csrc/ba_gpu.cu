@@ -217,8 +217,8 @@ struct Impl : ba_handle {
   DevBuf<int> d_view, d_point, d_pt_start, d_tile_pt, d_info;
   DevBuf<int> d_slot, d_cam_start, d_blk_a, d_blk_b, d_blk_start, d_counter;  // static structure of the deterministic Schur gather
   DevBuf<int2> d_pairs;
-  DevBuf<int> d_unit_pt, d_big_pt;  // warp units (points with <= 32 observations) / tiles of the larger points
-  int nunits = 0, nbig = 0;
+  DevBuf<int> d_unit_pt, d_big_pt, d_huge_pt;  // warp units (points with <= 32 observations) / tiles of the larger points / points with > TILE observations
+  int nunits = 0, nbig = 0, nhuge = 0, huge_max = 0;
   DevBuf<T> d_P, d_D, d_Pt;  // per-observation (P, D) / per-point records written by k_point_factor*
   int nblocks = 0, gather_grid = 0;
   DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g | gJ */, d_keep, d_dvec, d_tmp;
@@ -285,26 +285,35 @@ struct Impl : ba_handle {
     }
     for (int j = 0; j < M; ++j) {
       if (pt_start[j + 1] < 1) return fail(BA_ERR_ARG, "point %d has no observation", j);
-      if (pt_start[j + 1] > TILE) return fail(BA_ERR_ARG, "point %d has %d observations; this build supports at most %d per point", j, pt_start[j + 1], TILE);
+      if (pt_start[j + 1] > BIG_POINT_MAX) return fail(BA_ERR_ARG, "point %d has %d observations; this build supports at most %d per point", j, pt_start[j + 1], BIG_POINT_MAX);
       pt_start[j + 1] += pt_start[j];
     }
     bw = 0;
     for (int j = 0; j < M; ++j) bw = std::max(bw, view[pt_start[j + 1] - 1] - view[pt_start[j]]);
-    std::vector<int> tile_pt; tile_pt.push_back(0);
-    int cur_obs = 0, cur_pts = 0;
-    for (int j = 0; j < M; ++j) {
-      const int nj = pt_start[j + 1] - pt_start[j];
-      if (cur_obs + nj > TILE || cur_pts + 1 > TILE) { tile_pt.push_back(j); cur_obs = 0; cur_pts = 0; }
-      cur_obs += nj; cur_pts++;
+    // back-substitution tiles: (first, end) pairs of consecutive points whose observations fit TILE lanes; a point
+    // with more than TILE observations ("huge": long tracks of real BAL files) gets its own CTA in separate kernels
+    std::vector<int> tile_pt, huge_pt;
+    {
+      int first = 0, cur_obs = 0, cur_pts = 0;
+      auto close = [&](int end) { if (end > first) { tile_pt.push_back(first); tile_pt.push_back(end); } };
+      for (int j = 0; j < M; ++j) {
+        const int nj = pt_start[j + 1] - pt_start[j];
+        if (nj > TILE) { close(j); huge_pt.push_back(j); first = j + 1; cur_obs = 0; cur_pts = 0; continue; }
+        if (cur_obs + nj > TILE || cur_pts + 1 > TILE) { close(j); first = j; cur_obs = 0; cur_pts = 0; }
+        cur_obs += nj; cur_pts++;
+      }
+      close(M);
     }
-    tile_pt.push_back(M);
-    ntiles = (int)tile_pt.size() - 1;
+    nhuge = (int)huge_pt.size();
+    for (int j : huge_pt) huge_max = std::max(huge_max, pt_start[j + 1] - pt_start[j]);
+    ntiles = (int)tile_pt.size() / 2;
 
     // point factor work units: one warp per run of consecutive points whose observations fit 32 lanes
     // (k_point_factor_warp); a point with more than 32 observations becomes its own shared-memory tile
     std::vector<int> unit_pt, big_pt;
     for (int j = 0; j < M;) {
       const int nj = pt_start[j + 1] - pt_start[j];
+      if (nj > TILE) { ++j; continue; }  // huge point: k_point_factor_big
       if (nj > 32) { big_pt.push_back(j); big_pt.push_back(j + 1); ++j; continue; }
       int j1 = j, cnt = 0;
       while (j1 < M && pt_start[j1 + 1] - pt_start[j1] <= 32 && cnt + (pt_start[j1 + 1] - pt_start[j1]) <= 32) { cnt += pt_start[j1 + 1] - pt_start[j1]; ++j1; }
@@ -356,18 +365,22 @@ struct Impl : ba_handle {
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) CK(cudaEventCreate(&e));
-    CK(d_view.alloc(K)); CK(d_point.alloc(K)); CK(d_pt_start.alloc(M + 1)); CK(d_tile_pt.alloc(ntiles + 1)); CK(d_info.alloc(1));
+    CK(d_view.alloc(K)); CK(d_point.alloc(K)); CK(d_pt_start.alloc(M + 1)); CK(d_tile_pt.alloc(2 * (size_t)ntiles + 2)); CK(d_huge_pt.alloc(nhuge + 1)); CK(d_info.alloc(1));
     CK(d_meas.alloc(2 * (size_t)K));
     CK(d_cams.alloc((size_t)N * CAM_STRIDE)); CK(d_cams_test.alloc((size_t)N * CAM_STRIDE));
     CK(d_X.alloc(3 * (size_t)M)); CK(d_X_test.alloc(3 * (size_t)M));
     CK(d_dx_pt.alloc(3 * (size_t)M)); CK(d_dx_cam.alloc(9 * (size_t)N));
-    const size_t npart = std::max<size_t>(3 * (size_t)ntiles, (size_t)(K + 255) / 256);
+    const size_t npart = std::max<size_t>(3 * (size_t)(ntiles + nhuge), (size_t)(K + 255) / 256);
     CK(d_partials.alloc(npart)); CK(d_scal.alloc(16)); CK(d_dbg.alloc(16)); CK(cudaMemset(d_dbg.p, 0, 16 * sizeof(long long)));
     CK(cudaMallocHost(&h_scal, 16 * sizeof(double)));
     CK(cudaMemcpyAsync(d_view.p, view, K * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_point.p, point, K * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_pt_start.p, pt_start.data(), (M + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(d_tile_pt.p, tile_pt.data(), (ntiles + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (ntiles) CK(cudaMemcpyAsync(d_tile_pt.p, tile_pt.data(), tile_pt.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (nhuge) {
+      CK(cudaMemcpyAsync(d_huge_pt.p, huge_pt.data(), nhuge * sizeof(int), cudaMemcpyHostToDevice, stream));
+      CK(cudaFuncSetAttribute(k_point_factor_big<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_point_smem_bytes<T>(huge_max)));
+    }
     CK(d_unit_pt.alloc(unit_pt.size())); CK(d_big_pt.alloc(big_pt.size()));
     if (nunits) CK(cudaMemcpyAsync(d_unit_pt.p, unit_pt.data(), unit_pt.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
     if (nbig) CK(cudaMemcpyAsync(d_big_pt.p, big_pt.data(), big_pt.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -566,6 +579,10 @@ struct Impl : ba_handle {
       TileArgs<T> ab = tile_args(lamT); ab.tile_pt = d_big_pt.p;
       k_point_factor<T><<<nbig, TILE, sizeof(TileSmem<T>), stream>>>(ab, 2, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++;
     }
+    if (nhuge) {
+      k_point_factor_big<T><<<nhuge, BIG_THREADS, big_point_smem_bytes<T>(huge_max), stream>>>(tile_args(lamT), d_huge_pt.p, d_slot.p, d_P.p, d_D.p, d_Pt.p);
+      launches++;
+    }
     CK(cudaGetLastError());
     mark(1);
     CK(cudaMemsetAsync(d_counter.p, 0, sizeof(int), stream));
@@ -738,12 +755,18 @@ struct Impl : ba_handle {
     k_cam_update<T><<<1, 1024, 0, stream>>>(N, d_cams.p, d_dx_cam.p, gJvec(), d_cams_test.p, d_scal.p + 4, d_scal.p + 6);
     launches++;
     mark(6);
-    k_backsub_eval<T><<<ntiles, TILE, backsub_smem_bytes<T>(), stream>>>(tile_args(lamT), d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
-                                                    d_partials.p, ntiles);
-    launches++;
+    const int ntot = ntiles + nhuge;
+    if (ntiles)
+      k_backsub_eval<T><<<ntiles, TILE, backsub_smem_bytes<T>(), stream>>>(tile_args(lamT), d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
+                                                      d_partials.p, ntot);
+    if (nhuge)
+      k_backsub_big<T><<<nhuge, BIG_THREADS, 0, stream>>>(tile_args(lamT), d_huge_pt.p, d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
+                                                          d_partials.p, ntiles, ntot);
+    launches += (ntiles ? 1 : 0) + (nhuge ? 1 : 0);
+
     CK(cudaGetLastError());
     mark(7);
-    k_reduce<<<3, 256, 0, stream>>>(d_partials.p, ntiles, d_scal.p + 1);
+    k_reduce<<<3, 256, 0, stream>>>(d_partials.p, ntot, d_scal.p + 1);
     launches++;
     int rc = allreduce_scal(1, 3);
     if (rc) return rc;

@@ -38,17 +38,29 @@ template <class T> struct TileSmem {
   int ptObs0[TP];  // per point: first local observation
   int ptN[TP];     // per point: observation count
   double red[3 * (TILE / 32)];
+  __device__ static constexpr int stride() { return TP; }
+  __device__ static constexpr int ostride() { return TP; }
+};
+// One point per CTA (more than TILE observations): Q / E rows in dynamic shared memory with a runtime stride,
+// the point's outputs (p = 0) in small arrays.
+template <class T> struct BigPointStore {
+  T* Q; T* E; int st;
+  T Rm[6], C[3], G[3]; int perm[1];
+  __device__ int stride() const { return st; }
+  __device__ static constexpr int ostride() { return 1; }
 };
 
 // ---------------------------------------------------------------------------------------------
 // Phase 2: one lane per point. Rows rho = 2*i + a live in sm.Q[(3a+b)*TP + lo + i]; the three
 // lambda rows sqrt(lambda) I3 live in registers. Eigen ColPivHouseholderQR conventions.
 // ---------------------------------------------------------------------------------------------
-template <class T>
-__device__ __forceinline__ T& qel(TileSmem<T>& sm, int lo, int rho, int b) { return sm.Q[(3 * (rho & 1) + b) * TP + lo + (rho >> 1)]; }
+// The storage is a template parameter: TileSmem (stride TP, one lane per point) or BigPointStore (one point per CTA,
+// runtime stride; points with more than TILE observations).
+template <class T, class S>
+__device__ __forceinline__ T& qel(S& sm, int lo, int rho, int b) { return sm.Q[(3 * (rho & 1) + b) * sm.stride() + lo + (rho >> 1)]; }
 
-template <class T>
-__device__ void point_householder(TileSmem<T>& sm, int p, int lo, int n, T sl) {
+template <class T, class S>
+__device__ void point_householder(S& sm, int p, int lo, int n, T sl) {
   const int m = 2 * n;  // observation rows; plus 3 register rows
   T L[3][3] = {{sl, T(0), T(0)}, {T(0), sl, T(0)}, {T(0), T(0), sl}};
   T tau[3] = {T(0), T(0), T(0)};
@@ -58,12 +70,12 @@ __device__ void point_householder(TileSmem<T>& sm, int p, int lo, int n, T sl) {
   {
     T g0 = T(0), g1 = T(0), g2 = T(0);
     for (int i = 0; i < n; ++i) {
-      const T e0 = sm.E[lo + i], e1 = sm.E[TP + lo + i];
-      g0 += sm.Q[0 * TP + lo + i] * e0 + sm.Q[3 * TP + lo + i] * e1;
-      g1 += sm.Q[1 * TP + lo + i] * e0 + sm.Q[4 * TP + lo + i] * e1;
-      g2 += sm.Q[2 * TP + lo + i] * e0 + sm.Q[5 * TP + lo + i] * e1;
+      const T e0 = sm.E[lo + i], e1 = sm.E[sm.stride() + lo + i];
+      g0 += sm.Q[0 * sm.stride() + lo + i] * e0 + sm.Q[3 * sm.stride() + lo + i] * e1;
+      g1 += sm.Q[1 * sm.stride() + lo + i] * e0 + sm.Q[4 * sm.stride() + lo + i] * e1;
+      g2 += sm.Q[2 * sm.stride() + lo + i] * e0 + sm.Q[5 * sm.stride() + lo + i] * e1;
     }
-    sm.G[p] = g0; sm.G[TP + p] = g1; sm.G[2 * TP + p] = g2;
+    sm.G[p] = g0; sm.G[sm.ostride() + p] = g1; sm.G[2 * sm.ostride() + p] = g2;
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -73,7 +85,7 @@ __device__ void point_householder(TileSmem<T>& sm, int p, int lo, int n, T sl) {
     for (int c = 0; c < 3; ++c) {
       if (c < k) continue;
       T s = T(0);
-      for (int r = k; r < m; ++r) { const T v = qel(sm, lo, r, c); s += v * v; }
+      for (int r = k; r < m; ++r) { const T v = qel<T>(sm, lo, r, c); s += v * v; }
 #pragma unroll
       for (int r = 0; r < 3; ++r) s += L[r][c] * L[r][c];
       nn[c] = s;
@@ -82,7 +94,7 @@ __device__ void point_householder(TileSmem<T>& sm, int p, int lo, int n, T sl) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) if (c > k && nn[c] > nn[best]) best = c;
     if (best != k) {
-      for (int r = 0; r < m; ++r) { T& a = qel(sm, lo, r, k); T& b = qel(sm, lo, r, best); const T t = a; a = b; b = t; }
+      for (int r = 0; r < m; ++r) { T& a = qel<T>(sm, lo, r, k); T& b = qel<T>(sm, lo, r, best); const T t = a; a = b; b = t; }
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -94,49 +106,49 @@ __device__ void point_householder(TileSmem<T>& sm, int p, int lo, int n, T sl) {
       if (k == 0) pm0 = pb; else if (k == 1) pm1 = pb; else pm2 = pb;
       if (best == 1) pm1 = pk; else pm2 = pk;
     }
-    const T c0 = qel(sm, lo, k, k);
+    const T c0 = qel<T>(sm, lo, k, k);
     T tail2 = T(0);
-    for (int r = k + 1; r < m; ++r) { const T v = qel(sm, lo, r, k); tail2 += v * v; }
+    for (int r = k + 1; r < m; ++r) { const T v = qel<T>(sm, lo, r, k); tail2 += v * v; }
 #pragma unroll
     for (int r = 0; r < 3; ++r) tail2 += L[r][k] * L[r][k];
     T beta, tk;
     if (tail2 <= (sizeof(T) == 8 ? T(2.2250738585072014e-308) : T(1.17549435e-38f))) {
       tk = T(0); beta = c0;
-      for (int r = k + 1; r < m; ++r) qel(sm, lo, r, k) = T(0);
+      for (int r = k + 1; r < m; ++r) qel<T>(sm, lo, r, k) = T(0);
 #pragma unroll
       for (int r = 0; r < 3; ++r) L[r][k] = T(0);
     } else {
       beta = tsqrt(c0 * c0 + tail2);
       if (c0 >= T(0)) beta = -beta;
       const T inv = T(1) / (c0 - beta);
-      for (int r = k + 1; r < m; ++r) qel(sm, lo, r, k) *= inv;
+      for (int r = k + 1; r < m; ++r) qel<T>(sm, lo, r, k) *= inv;
 #pragma unroll
       for (int r = 0; r < 3; ++r) L[r][k] *= inv;
       tk = (beta - c0) / beta;
     }
     tau[k] = tk;
-    qel(sm, lo, k, k) = beta;
+    qel<T>(sm, lo, k, k) = beta;
     // apply H_k to the remaining columns
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       if (c <= k) continue;
-      T s = qel(sm, lo, k, c);
-      for (int r = k + 1; r < m; ++r) s += qel(sm, lo, r, k) * qel(sm, lo, r, c);
+      T s = qel<T>(sm, lo, k, c);
+      for (int r = k + 1; r < m; ++r) s += qel<T>(sm, lo, r, k) * qel<T>(sm, lo, r, c);
 #pragma unroll
       for (int r = 0; r < 3; ++r) s += L[r][k] * L[r][c];
       s *= tk;
-      qel(sm, lo, k, c) -= s;
-      for (int r = k + 1; r < m; ++r) qel(sm, lo, r, c) -= s * qel(sm, lo, r, k);
+      qel<T>(sm, lo, k, c) -= s;
+      for (int r = k + 1; r < m; ++r) qel<T>(sm, lo, r, c) -= s * qel<T>(sm, lo, r, k);
 #pragma unroll
       for (int r = 0; r < 3; ++r) L[r][c] -= s * L[r][k];
     }
   }
   // R (upper triangle) sits in observation rows 0..2 (n >= 2 => m >= 4); column swaps above were
   // applied to all rows, so it is already in pivoted column order.
-  Rv[0] = qel(sm, lo, 0, 0); Rv[1] = qel(sm, lo, 0, 1); Rv[2] = qel(sm, lo, 0, 2);
-  Rv[3] = qel(sm, lo, 1, 1); Rv[4] = qel(sm, lo, 1, 2); Rv[5] = qel(sm, lo, 2, 2);
+  Rv[0] = qel<T>(sm, lo, 0, 0); Rv[1] = qel<T>(sm, lo, 0, 1); Rv[2] = qel<T>(sm, lo, 0, 2);
+  Rv[3] = qel<T>(sm, lo, 1, 1); Rv[4] = qel<T>(sm, lo, 1, 2); Rv[5] = qel<T>(sm, lo, 2, 2);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) sm.Rm[i * TP + p] = Rv[i];
+  for (int i = 0; i < 6; ++i) sm.Rm[i * sm.ostride() + p] = Rv[i];
   sm.perm[p] = pm0 | (pm1 << 2) | (pm2 << 4);
   // form the thin Q1 in place (dorg2r): k = 2, 1, 0
 #pragma unroll
@@ -145,71 +157,71 @@ __device__ void point_householder(TileSmem<T>& sm, int p, int lo, int n, T sl) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       if (c <= k) continue;
-      T s = qel(sm, lo, k, c);
-      for (int r = k + 1; r < m; ++r) s += qel(sm, lo, r, k) * qel(sm, lo, r, c);
+      T s = qel<T>(sm, lo, k, c);
+      for (int r = k + 1; r < m; ++r) s += qel<T>(sm, lo, r, k) * qel<T>(sm, lo, r, c);
 #pragma unroll
       for (int r = 0; r < 3; ++r) s += L[r][k] * L[r][c];
       s *= tk;
-      qel(sm, lo, k, c) -= s;
-      for (int r = k + 1; r < m; ++r) qel(sm, lo, r, c) -= s * qel(sm, lo, r, k);
+      qel<T>(sm, lo, k, c) -= s;
+      for (int r = k + 1; r < m; ++r) qel<T>(sm, lo, r, c) -= s * qel<T>(sm, lo, r, k);
 #pragma unroll
       for (int r = 0; r < 3; ++r) L[r][c] -= s * L[r][k];
     }
-    for (int r = k + 1; r < m; ++r) qel(sm, lo, r, k) *= -tk;
+    for (int r = k + 1; r < m; ++r) qel<T>(sm, lo, r, k) *= -tk;
 #pragma unroll
     for (int r = 0; r < 3; ++r) L[r][k] *= -tk;
-    qel(sm, lo, k, k) = T(1) - tk;
-    for (int r = 0; r < k; ++r) qel(sm, lo, r, k) = T(0);
+    qel<T>(sm, lo, k, k) = T(1) - tk;
+    for (int r = 0; r < k; ++r) qel<T>(sm, lo, r, k) = T(0);
   }
   // c = Q1^T e
   T c0 = T(0), c1 = T(0), c2 = T(0);
   for (int i = 0; i < n; ++i) {
-    const T e0 = sm.E[lo + i], e1 = sm.E[TP + lo + i];
-    c0 += sm.Q[0 * TP + lo + i] * e0 + sm.Q[3 * TP + lo + i] * e1;
-    c1 += sm.Q[1 * TP + lo + i] * e0 + sm.Q[4 * TP + lo + i] * e1;
-    c2 += sm.Q[2 * TP + lo + i] * e0 + sm.Q[5 * TP + lo + i] * e1;
+    const T e0 = sm.E[lo + i], e1 = sm.E[sm.stride() + lo + i];
+    c0 += sm.Q[0 * sm.stride() + lo + i] * e0 + sm.Q[3 * sm.stride() + lo + i] * e1;
+    c1 += sm.Q[1 * sm.stride() + lo + i] * e0 + sm.Q[4 * sm.stride() + lo + i] * e1;
+    c2 += sm.Q[2 * sm.stride() + lo + i] * e0 + sm.Q[5 * sm.stride() + lo + i] * e1;
   }
-  sm.C[p] = c0; sm.C[TP + p] = c1; sm.C[2 * TP + p] = c2;
+  sm.C[p] = c0; sm.C[sm.ostride() + p] = c1; sm.C[2 * sm.ostride() + p] = c2;
 }
 
 // Normal-equation point factor (CHOLESKY variant, BacktrackLevMarqCholesky.h:260-282):
 // V = Jp^T Jp + lambda I = L D L^T; R := D^{1/2} L^T; Q1 rows := Jp rows * R^{-1}.
-template <class T>
-__device__ void point_normal(TileSmem<T>& sm, int p, int lo, int n, T lambda) {
+template <class T, class S>
+__device__ void point_normal(S& sm, int p, int lo, int n, T lambda) {
   T v00 = lambda, v10 = T(0), v11 = lambda, v20 = T(0), v21 = T(0), v22 = lambda;
   T g0 = T(0), g1 = T(0), g2 = T(0);
   for (int i = 0; i < n; ++i) {
-    const T a0 = sm.Q[0 * TP + lo + i], a1 = sm.Q[1 * TP + lo + i], a2 = sm.Q[2 * TP + lo + i];
-    const T b0 = sm.Q[3 * TP + lo + i], b1 = sm.Q[4 * TP + lo + i], b2 = sm.Q[5 * TP + lo + i];
-    const T e0 = sm.E[lo + i], e1 = sm.E[TP + lo + i];
+    const T a0 = sm.Q[0 * sm.stride() + lo + i], a1 = sm.Q[1 * sm.stride() + lo + i], a2 = sm.Q[2 * sm.stride() + lo + i];
+    const T b0 = sm.Q[3 * sm.stride() + lo + i], b1 = sm.Q[4 * sm.stride() + lo + i], b2 = sm.Q[5 * sm.stride() + lo + i];
+    const T e0 = sm.E[lo + i], e1 = sm.E[sm.stride() + lo + i];
     v00 += a0 * a0 + b0 * b0; v10 += a1 * a0 + b1 * b0; v11 += a1 * a1 + b1 * b1;
     v20 += a2 * a0 + b2 * b0; v21 += a2 * a1 + b2 * b1; v22 += a2 * a2 + b2 * b2;
     g0 += a0 * e0 + b0 * e1; g1 += a1 * e0 + b1 * e1; g2 += a2 * e0 + b2 * e1;
   }
-  sm.G[p] = g0; sm.G[TP + p] = g1; sm.G[2 * TP + p] = g2;
+  sm.G[p] = g0; sm.G[sm.ostride() + p] = g1; sm.G[2 * sm.ostride() + p] = g2;
   const T d0 = v00, l10 = v10 / d0, l20 = v20 / d0;
   const T d1 = v11 - l10 * l10 * d0, l21 = (v21 - l20 * l10 * d0) / d1;
   const T d2 = v22 - l20 * l20 * d0 - l21 * l21 * d1;
   const T s0 = tsqrt(d0), s1 = tsqrt(d1), s2 = tsqrt(d2);
   const T r00 = s0, r01 = s0 * l10, r02 = s0 * l20, r11 = s1, r12 = s1 * l21, r22 = s2;
-  sm.Rm[0 * TP + p] = r00; sm.Rm[1 * TP + p] = r01; sm.Rm[2 * TP + p] = r02;
-  sm.Rm[3 * TP + p] = r11; sm.Rm[4 * TP + p] = r12; sm.Rm[5 * TP + p] = r22;
+  sm.Rm[0 * sm.ostride() + p] = r00; sm.Rm[1 * sm.ostride() + p] = r01; sm.Rm[2 * sm.ostride() + p] = r02;
+  sm.Rm[3 * sm.ostride() + p] = r11; sm.Rm[4 * sm.ostride() + p] = r12; sm.Rm[5 * sm.ostride() + p] = r22;
   sm.perm[p] = 0 | (1 << 2) | (2 << 4);
   const T i00 = T(1) / r00, i11 = T(1) / r11, i22 = T(1) / r22;
   T c0 = T(0), c1 = T(0), c2 = T(0);
   for (int i = 0; i < n; ++i) {
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
-      const T x0 = sm.Q[(3 * a + 0) * TP + lo + i], x1 = sm.Q[(3 * a + 1) * TP + lo + i], x2 = sm.Q[(3 * a + 2) * TP + lo + i];
+      const T x0 = sm.Q[(3 * a + 0) * sm.stride() + lo + i], x1 = sm.Q[(3 * a + 1) * sm.stride() + lo + i], x2 = sm.Q[(3 * a + 2) * sm.stride() + lo + i];
       const T q0 = x0 * i00;
       const T q1 = (x1 - q0 * r01) * i11;
       const T q2 = (x2 - q0 * r02 - q1 * r12) * i22;
-      sm.Q[(3 * a + 0) * TP + lo + i] = q0; sm.Q[(3 * a + 1) * TP + lo + i] = q1; sm.Q[(3 * a + 2) * TP + lo + i] = q2;
-      const T e = sm.E[a * TP + lo + i];
+      sm.Q[(3 * a + 0) * sm.stride() + lo + i] = q0; sm.Q[(3 * a + 1) * sm.stride() + lo + i] = q1; sm.Q[(3 * a + 2) * sm.stride() + lo + i] = q2;
+      const T e = sm.E[a * sm.stride() + lo + i];
       c0 += q0 * e; c1 += q1 * e; c2 += q2 * e;
     }
   }
-  sm.C[p] = c0; sm.C[TP + p] = c1; sm.C[2 * TP + p] = c2;
+  sm.C[p] = c0; sm.C[sm.ostride() + p] = c1; sm.C[2 * sm.ostride() + p] = c2;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -257,8 +269,8 @@ __device__ __forceinline__ void tile_phases_123(const TileArgs<T>& a, TileSmem<T
   __syncthreads();
   if (t < npts) {
     const int n = sm.ptN[t];
-    if (a.factor == PF_HOUSEHOLDER && n >= 2) point_householder<T>(sm, t, sm.ptObs0[t], n, tsqrt(a.lambda));
-    else point_normal<T>(sm, t, sm.ptObs0[t], n, a.lambda);
+    if (a.factor == PF_HOUSEHOLDER && n >= 2) point_householder<T, TileSmem<T>>(sm, t, sm.ptObs0[t], n, tsqrt(a.lambda));
+    else point_normal<T, TileSmem<T>>(sm, t, sm.ptObs0[t], n, a.lambda);
   }
   __syncthreads();
   if (t < nobs) {
@@ -917,7 +929,7 @@ __global__ void __launch_bounds__(TILE, 5) k_backsub_eval(TileArgs<T> a, const T
   __shared__ T sx[3][TP];
   __shared__ double red[3 * (TILE / 32)];
   const int t = threadIdx.x, tile = blockIdx.x, lane = t & 31, w0 = t & ~31;
-  const int p0 = __ldg(a.tile_pt + tile), p1 = __ldg(a.tile_pt + tile + 1), npts = p1 - p0;
+  const int p0 = __ldg(a.tile_pt + 2 * tile), p1 = __ldg(a.tile_pt + 2 * tile + 1), npts = p1 - p0;  // (first, end) pairs
   const int o0 = __ldg(a.pt_start + p0), nobs = __ldg(a.pt_start + p1) - o0;
   // Every warp stages the records and dx_cam rows of ITS 32 observations (lane = (record, chunk): one copy
   // instruction moves RPI whole records; the tile's records are contiguous), so a __syncwarp suffices before
@@ -1016,6 +1028,154 @@ __global__ void __launch_bounds__(TILE, 5) k_backsub_eval(TileArgs<T> a, const T
     double s = 0.0;
     for (int w = 0; w < TILE / 32; ++w) s += red[t * (TILE / 32) + w];
     partials[(size_t)t * ntiles + tile] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Points with more than TILE observations (long tracks in real BAL files): one CTA per point. The Jp rows and the
+// residual of all observations sit in dynamic shared memory (8 scalars per observation), the 3-column
+// factorisation is the same routine as in the tile kernel (one thread, serial: such points are rare), the camera
+// Jacobian is re-evaluated for the records. Same records, same conventions as k_point_factor_warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int BIG_THREADS = 256;
+constexpr int BIG_POINT_MAX = 3000;  // 8 scalars per observation in shared memory (192 KB in double)
+template <class T> constexpr size_t big_point_smem_bytes(int nmax) { return (size_t)8 * nmax * sizeof(T); }
+
+template <class T>
+__global__ void __launch_bounds__(BIG_THREADS) k_point_factor_big(TileArgs<T> a, const int* __restrict__ huge_pt, const int* __restrict__ slot,
+                                                                  T* __restrict__ Prec, T* __restrict__ Drec, T* __restrict__ Ptrec) {
+  extern __shared__ __align__(16) unsigned char big_smem_raw[];
+  __shared__ BigPointStore<T> st;
+  const int t = threadIdx.x, pj = __ldg(huge_pt + blockIdx.x);
+  const int o0 = __ldg(a.pt_start + pj), n = __ldg(a.pt_start + pj + 1) - o0;
+  if (t == 0) { st.Q = reinterpret_cast<T*>(big_smem_raw); st.E = st.Q + 6 * (size_t)n; st.st = n; }
+  __syncthreads();
+  const T X0 = __ldg(a.X + 3 * (size_t)pj), X1 = __ldg(a.X + 3 * (size_t)pj + 1), X2 = __ldg(a.X + 3 * (size_t)pj + 2);
+  for (int i = t; i < n; i += BIG_THREADS) {
+    const int o = o0 + i;
+    Cam<T> c; load_cam<T>(a.cams, __ldg(a.view + o), c);
+    T e0, e1, jc[18], jp[6];
+    obs_jacobian<T>(c, X0, X1, X2, __ldg(a.meas + 2 * (size_t)o), __ldg(a.meas + 2 * (size_t)o + 1), a.tau2, e0, e1, jc, jp);
+    st.E[i] = e0; st.E[n + i] = e1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) st.Q[(size_t)k * n + i] = jp[k];
+  }
+  __syncthreads();
+  if (t == 0) {
+    if (a.factor == PF_HOUSEHOLDER && n >= 2) point_householder<T, BigPointStore<T>>(st, 0, 0, n, tsqrt(a.lambda));
+    else point_normal<T, BigPointStore<T>>(st, 0, 0, n, a.lambda);
+  }
+  __syncthreads();
+  const T c0 = st.C[0], c1 = st.C[1], c2 = st.C[2];
+  for (int i = t; i < n; i += BIG_THREADS) {
+    const int o = o0 + i;
+    Cam<T> c; load_cam<T>(a.cams, __ldg(a.view + o), c);
+    T e0, e1, jc[18], jp[6];
+    obs_jacobian<T>(c, X0, X1, X2, __ldg(a.meas + 2 * (size_t)o), __ldg(a.meas + 2 * (size_t)o + 1), a.tau2, e0, e1, jc, jp);
+    T q[2][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { q[0][k] = st.Q[(size_t)k * n + i]; q[1][k] = st.Q[(size_t)(3 + k) * n + i]; }
+    T rec[REC];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int b = 0; b < 9; ++b) rec[9 * k + b] = q[0][k] * jc[b] + q[1][k] * jc[9 + b];
+    rec[27] = T(0);
+    store_rec(Prec + (size_t)o * REC, rec);
+#pragma unroll
+    for (int b = 0; b < 18; ++b) rec[b] = jc[b];
+    fill_drec_tail<T>(rec, q[0][0], q[0][1], q[0][2], q[1][0], q[1][1], q[1][2], c0, c1, c2, e0, e1);
+    store_rec(Drec + (size_t)__ldg(slot + o) * REC, rec);
+  }
+  if (t == 0) {
+    T* q = Ptrec + (size_t)pj * PREC;
+    store4(q, st.Rm[0], st.Rm[1], st.Rm[2], st.Rm[3]);
+    store4(q + 4, st.Rm[4], st.Rm[5], st.C[0], st.C[1]);
+    store4(q + 8, st.C[2], st.G[0], st.G[1], st.G[2]);
+    store4(q + 12, (T)st.perm[0], T(0), T(0), T(0));
+  }
+}
+
+// fixed-order block sum of three doubles (BIG_THREADS threads); result valid in thread 0
+__device__ __forceinline__ void big_block_sum3(double& a0, double& a1, double& a2, double* red) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a0 += __shfl_down_sync(0xffffffffu, a0, off);
+    a1 += __shfl_down_sync(0xffffffffu, a1, off);
+    a2 += __shfl_down_sync(0xffffffffu, a2, off);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) { red[warp] = a0; red[8 + warp] = a1; red[16 + warp] = a2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a0 = a1 = a2 = 0.0;
+    for (int w = 0; w < BIG_THREADS / 32; ++w) { a0 += red[w]; a1 += red[8 + w]; a2 += red[16 + w]; }
+  }
+}
+
+// back-substitution + update + test energy of one point with more than TILE observations (k_backsub_eval's job);
+// partial sums go to tile slot `tile0 + blockIdx.x` of the same partials array.
+template <class T>
+__global__ void __launch_bounds__(BIG_THREADS) k_backsub_big(TileArgs<T> a, const int* __restrict__ huge_pt, const T* __restrict__ Prec,
+                                                             const T* __restrict__ Ptrec, const T* __restrict__ dx_cam, const T* __restrict__ cams_test,
+                                                             T* __restrict__ dx_pt, T* __restrict__ X_test, double* __restrict__ partials, int tile0,
+                                                             int ntiles) {
+  __shared__ double red[24];
+  __shared__ T sx[3];
+  const int t = threadIdx.x, pj = __ldg(huge_pt + blockIdx.x);
+  const int o0 = __ldg(a.pt_start + pj), n = __ldg(a.pt_start + pj + 1) - o0;
+  double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+  for (int i = t; i < n; i += BIG_THREADS) {
+    const int o = o0 + i;
+    const T* pr = Prec + (size_t)o * REC;
+    const T* d = dx_cam + 9 * (size_t)__ldg(a.view + o);
+    T dd[9];
+#pragma unroll
+    for (int b = 0; b < 9; ++b) dd[b] = __ldg(d + b);
+    T v[3] = {T(0), T(0), T(0)};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int b = 0; b < 9; ++b) v[k] += __ldg(pr + 9 * k + b) * dd[b];
+    u0 += (double)v[0]; u1 += (double)v[1]; u2 += (double)v[2];
+  }
+  big_block_sum3(u0, u1, u2, red);
+  double acc_e = 0.0, acc_dx = 0.0, acc_jd = 0.0;
+  if (t == 0) {
+    const T* q = Ptrec + (size_t)pj * PREC;
+    T R00, R01, R02, R11, R12v, R22, c0, c1, c2, G0, G1, G2, pf, z_, z1_, z2_;
+    load4(q, R00, R01, R02, R11);
+    load4(q + 4, R12v, R22, c0, c1);
+    load4(q + 8, c2, G0, G1, G2);
+    load4(q + 12, pf, z_, z1_, z2_);
+    const T r0 = -c0 - (T)u0, r1 = -c1 - (T)u1, r2 = -c2 - (T)u2;
+    const T z2 = r2 / R22;
+    const T z1 = (r1 - R12v * z2) / R11;
+    const T z0 = (r0 - R01 * z1 - R02 * z2) / R00;
+    const int pm = (int)pf;
+    T d[3];
+    d[pm & 3] = z0; d[(pm >> 2) & 3] = z1; d[(pm >> 4) & 3] = z2;
+    const size_t gp = 3 * (size_t)pj;
+    acc_dx = (double)(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    acc_jd = (double)(G0 * d[0] + G1 * d[1] + G2 * d[2]);
+    dx_pt[gp] = d[0]; dx_pt[gp + 1] = d[1]; dx_pt[gp + 2] = d[2];
+    const T x0 = __ldg(a.X + gp) + d[0], x1 = __ldg(a.X + gp + 1) + d[1], x2 = __ldg(a.X + gp + 2) + d[2];
+    X_test[gp] = x0; X_test[gp + 1] = x1; X_test[gp + 2] = x2;
+    sx[0] = x0; sx[1] = x1; sx[2] = x2;
+  }
+  __syncthreads();
+  for (int i = t; i < n; i += BIG_THREADS) {
+    const int o = o0 + i;
+    Cam<T> c; load_cam<T>(cams_test, __ldg(a.view + o), c);
+    T e0, e1;
+    obs_residual<T>(c, sx[0], sx[1], sx[2], __ldg(a.meas + 2 * (size_t)o), __ldg(a.meas + 2 * (size_t)o + 1), a.tau2, e0, e1);
+    acc_e += (double)(e0 * e0 + e1 * e1);
+  }
+  big_block_sum3(acc_e, acc_dx, acc_jd, red);
+  if (t == 0) {
+    const size_t idx = (size_t)tile0 + blockIdx.x;
+    partials[idx] = acc_e; partials[(size_t)ntiles + idx] = acc_dx; partials[2 * (size_t)ntiles + idx] = acc_jd;
   }
 }
 

@@ -94,3 +94,41 @@ def test_band_solve_float():
         ref = np.linalg.solve(A, g)
         assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 2e-5, (n, kd)
     s.close()
+
+
+@pytest.mark.parametrize("n,kd,one_cta", [(800, 700, False), (2313, 300, False), (351, 98, True), (1003, 548, True)])
+def test_band_qr_paths(n, kd, one_cta):
+    """Householder QR of the reduced camera block (QRKIT / MOREQR right block, BAFunctor.h:101,111): the global-memory
+    fallback (kd + 8 > 640), the look-ahead / compact-WY kernel on a larger ragged system (last panel narrower than 8
+    columns), and the single-CTA back substitution next to the cluster one."""
+    if one_cta:
+        os.environ["BA_QR_SOLVE_1CTA"] = "1"
+    try:
+        s = _solve("QRKIT", "f64", False)
+        A, g = band_spd(n, kd, 500 + n)
+        y = s.debug_band_solve(A, g, kd)
+    finally:
+        os.environ.pop("BA_QR_SOLVE_1CTA", None)
+    ref = np.linalg.solve(A, g)
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 1e-12, (n, kd)
+    s.close()
+
+
+def test_band_qr_unsymmetric_scaling_and_float():
+    """QR does not need definiteness: a symmetric indefinite band system; and the float instantiation."""
+    s = _solve("QRKIT", "f64", False)
+    n, kd = 420, 60
+    A, g = band_spd(n, kd, 11)
+    sgn = np.where(np.arange(n) % 4 == 0, -1.0, 1.0)
+    A = A * sgn[:, None] * sgn[None, :] - 2.0 * np.diag(np.diag(A)) * (np.arange(n) % 5 == 0)
+    y = s.debug_band_solve(A, g, kd)
+    ref = np.linalg.solve(A, g)
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 1e-10
+    s.close()
+    s = _solve("QRKIT", "f32", False)
+    for i, (n, kd) in enumerate(CASES[:7]):
+        A, g = band_spd(n, kd, 600 + i)
+        y = s.debug_band_solve(A, g, kd)
+        ref = np.linalg.solve(A, g)
+        assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 5e-5, (n, kd)
+    s.close()

@@ -229,10 +229,59 @@ def test_edge_cases_gpu():
         assert rel(Sg, So) < 1e-11
         assert relv(etb, ob.energy_at(dxb)) < 1e-9
         sb.close()
-    # rejected input: unsorted / duplicate observations, too many observations on one point
+    # rejected input: unsorted / duplicate observations
     bad = p.copy(); bad.view = p.view[::-1].copy(); bad.point = p.point[::-1].copy()
     with pytest.raises(solver.BAError):
         solver.GpuSolver(bad, "QRCHOL")
+
+
+def _long_track_problem():
+    """320 cameras; 300 ordinary points (2-12 observations), 30 points with 33-128 and 10 points with 150-319
+    observations (long tracks of real BAL files): the three point-factor paths in one problem. The three sets share
+    the camera truth (same seed and camera count -> same leading random draws in the generator)."""
+    N = 320
+    parts = [bal.synthetic_file_arrays(N, 300, seed=21, mean_obs=5.0, window=30),
+             bal.synthetic_file_arrays(N, 30, seed=21, mean_obs=80.0, window=100),
+             bal.synthetic_file_arrays(N, 10, seed=21, mean_obs=240.0, window=159)]
+    view = np.concatenate([q[0] for q in parts])
+    off = np.cumsum([0] + [len(q[4]) for q in parts])
+    point = np.concatenate([q[1] + off[i] for i, q in enumerate(parts)]).astype(np.int32)
+    meas = np.concatenate([q[2] for q in parts])
+    X = np.concatenate([q[4] for q in parts])
+    return bal.from_file_params(view, point, meas, parts[0][3], X, name="long-tracks")
+
+
+def test_long_tracks_all_variants():
+    """Points with more than 128 observations take k_point_factor_big / k_backsub_big (one CTA per point); same
+    reduced system, step and test energy as the oracle (per-point ColPivHouseholderQR of a (2n+3) x 3 block with
+    n up to 319, QRChol.h:319; 3x3 LDL^T for CHOLESKY). QRCHOL and CHOLESKY cover the two point factorisations; the
+    QR right block is independent of the track length (and its dense CPU oracle takes minutes at 320 cameras)."""
+    pb = _long_track_problem()
+    counts = np.bincount(pb.point)
+    assert counts.max() > 128 and ((counts > 32) & (counts <= 128)).any() and counts.min() <= 32
+    ob = Oracle(pb)
+    eb, cn2b, cnb = ob.linearize()
+    for variant in ("QRCHOL", "CHOLESKY"):
+        sb = solver.GpuSolver(pb, variant)
+        sb.keep_reduced(True)
+        eg, _, _ = sb.linearize()
+        assert relv(eg, eb) < 1e-12
+        lamb = 1e-12 * cn2b
+        okb, dxb = ob.step(solver.VARIANTS[variant], lamb)
+        So, go = ob.reduced()
+        sb.compute(lamb)
+        dxnb, _, etb = sb.solve_try()
+        Sg, gg = sb.reduced()
+        assert rel(Sg, So) < 1e-11
+        assert relv(dxnb, np.linalg.norm(dxb)) < 1e-7
+        assert relv(etb, ob.energy_at(dxb)) < 1e-9
+        sb.close()
+    sf = solver.GpuSolver(pb, "QRCHOL", "f32")
+    ef, cn2f, _ = sf.linearize()
+    sf.compute(1e-6 * cn2f)
+    dxf, _, etf = sf.solve_try()
+    assert np.isfinite(dxf) and np.isfinite(etf) and relv(ef, eb) < 1e-4
+    sf.close()
 
 
 def test_full_size_properties():
