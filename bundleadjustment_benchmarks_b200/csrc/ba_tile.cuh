@@ -554,6 +554,7 @@ __global__ void __launch_bounds__(TILE, BA_PF_MIN_BLOCKS) k_point_factor_warp(Ti
   const bool act = lane < un;
   const int o = o0 + (act ? lane : 0);
   const int cam_idx = __ldg(a.view + o), pj = __ldg(a.point + o);
+  const size_t sl = (size_t)__ldg(slot + o);   // consumed at the very end: issued with the first level of loads
   int s0 = lane, n = 1;
   if (act) { const int ps = __ldg(a.pt_start + pj); s0 = ps - o0; n = __ldg(a.pt_start + pj + 1) - ps; }
   const int i = lane - s0;
@@ -586,7 +587,6 @@ __global__ void __launch_bounds__(TILE, BA_PF_MIN_BLOCKS) k_point_factor_warp(Ti
     pm = pmh;
   }
   if (!act) return;
-  const size_t sl = (size_t)__ldg(slot + o);
   T rec[REC];
 #pragma unroll
   for (int k = 0; k < 3; ++k)
