@@ -708,6 +708,18 @@ struct Impl : ba_handle {
       const int want = 1 + (std::min(n - 1, 2 * kd) + 1 + QR_THREADS / 32 - 1) / (QR_THREADS / 32);  // panel CTA + one warp per trailing column
       const int grid = std::max(1, std::min(std::max(occ, 1) * sms, want));
       CK(cudaLaunchCooperativeKernel((void*)k_band_qr_reg<T>, dim3(grid), dim3(QR_THREADS), args, smem, stream));
+    } else if (kd + QR_PB <= 2560 && QrTallSmem<T>::bytes(kd) <= 200 * 1024 && !std::getenv("BA_QR_GLOBAL")) {
+      // columns too tall for registers (dense S of the larger bundled problems): streamed compact-WY updates
+      const size_t smem = QrTallSmem<T>::bytes(kd);
+      void* fn = (kd + QR_PB <= 1536) ? (void*)k_band_qr_tall<T, 6> : (void*)k_band_qr_tall<T, 10>;
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 0, sms = 0;
+      CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, QR_THREADS, smem));
+      const int want = 1 + (std::min(n - 1, 2 * kd) / 2 + 1 + QR_THREADS / 32 - 1) / (QR_THREADS / 32);  // panel CTA + one warp per two trailing columns
+      const int grid = std::max(1, std::min(std::max(occ, 1) * sms, want));
+      void* targs[] = {&Q, &tauv, &rhs, &Tg2};
+      CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(QR_THREADS), targs, smem, stream));
     } else {
       CK(cudaLaunchCooperativeKernel((void*)k_band_qr<T>, dim3(coop_grid_qr), dim3(QR_THREADS), args, 0, stream));
     }

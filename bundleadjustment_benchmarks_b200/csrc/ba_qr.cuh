@@ -383,7 +383,7 @@ __device__ __noinline__ void qr_apply_cta(const QRMat<T>& Q, const T* __restrict
 // from global memory). One block barrier per column: a single pass accumulates |tail|^2, the dot products with the
 // remaining columns and with the previous reflectors (for T); every thread then derives beta / tau redundantly and
 // updates its rows. Leaves the factored panel in sP (it becomes sV), in global memory, tau in tauv, T in sTout / Tg.
-template <class T>
+template <class T, int RPT>
 __device__ __noinline__ void qr_factor_panel(const QRMat<T>& Q, T* __restrict__ sP, T* __restrict__ spart, T* __restrict__ sG, T* __restrict__ sTout,
                                              T* __restrict__ tauv, T* __restrict__ Tg, const int LV, const int k0, const int pb,
                                              const int rows_staged) {
@@ -399,14 +399,14 @@ __device__ __noinline__ void qr_factor_panel(const QRMat<T>& Q, T* __restrict__ 
 #define FTICK(i) {}
 #endif
   T* sRow = spart + 128;   // [2][8] row c of every column, published by the thread that owns it
-  int ru[QR_RPT]; bool rin[QR_RPT];
+  int ru[RPT]; bool rin[RPT];
 #pragma unroll
-  for (int u = 0; u < QR_RPT; ++u) { const int r = tid + QR_THREADS * u; rin[u] = r < LV; ru[u] = min(r, LV - 1); }
-  T p[QR_PB][QR_RPT];
+  for (int u = 0; u < RPT; ++u) { const int r = tid + QR_THREADS * u; rin[u] = r < LV; ru[u] = min(r, LV - 1); }
+  T p[QR_PB][RPT];
 #pragma unroll
   for (int c = 0; c < QR_PB; ++c)
 #pragma unroll
-    for (int u = 0; u < QR_RPT; ++u) {
+    for (int u = 0; u < RPT; ++u) {
       const int r = ru[u], i = k0 + r, j = k0 + c;
       const bool inband = rin[u] && c < pb && i < n && i <= j + kd;
       T v = T(0);
@@ -425,11 +425,11 @@ __device__ __noinline__ void qr_factor_panel(const QRMat<T>& Q, T* __restrict__ 
         for (int q = 0; q < QR_PB; ++q) sRow[(c & 1) * 8 + q] = p[q][0];
       }
       // slot 0: |tail|^2; slots 1 .. 7-c: <tail, x_{c+s}>; slots 8-c .. 7: <tail, v_i>, i = s-(8-c)
-      T acc[QR_PB], vr[QR_RPT];
+      T acc[QR_PB], vr[RPT];
 #pragma unroll
       for (int q = 0; q < QR_PB; ++q) acc[q] = T(0);
 #pragma unroll
-      for (int u = 0; u < QR_RPT; ++u) {
+      for (int u = 0; u < RPT; ++u) {
         const bool ok = rin[u] && ru[u] > c && ru[u] <= rend;
         vr[u] = ok ? p[c][u] : T(0);
         acc[0] += vr[u] * vr[u];
@@ -468,7 +468,7 @@ __device__ __noinline__ void qr_factor_panel(const QRMat<T>& Q, T* __restrict__ 
       }
       FTICK(4)
 #pragma unroll
-      for (int u = 0; u < QR_RPT; ++u) {
+      for (int u = 0; u < RPT; ++u) {
         if (rin[u] && ru[u] > c && ru[u] <= rend) {
           const T vn = vr[u] * inv;   // tau == 0: inv == 0, the stored tail reads as zero (H = I)
           p[c][u] = vn;
@@ -504,9 +504,9 @@ __device__ __noinline__ void qr_factor_panel(const QRMat<T>& Q, T* __restrict__ 
 #pragma unroll
   for (int c = 0; c < QR_PB; ++c)
 #pragma unroll
-    for (int u = 0; u < QR_RPT; ++u) {
+    for (int u = 0; u < RPT; ++u) {
       const int r = ru[u], i = k0 + r, j = k0 + c;
-      if (rin[u]) sP[c * LV + r] = p[c][u];
+      if (sP != nullptr && rin[u]) sP[c * LV + r] = p[c][u];
       if (rin[u] && c < pb && i < n && i <= j + kd) Q.G[(size_t)j * Q.ld + (r - c + ku)] = p[c][u];
     }
   FTICK(6)
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(QR_THREADS) k_band_qr_reg(QRMat<T> Q, T* __res
   const bool panel_cta = blockIdx.x == 0;
   const int nupd = max(1, (int)gridDim.x - 1);     // CTAs that update trailing columns (all of them when the grid is one CTA)
   const int ucta = (gridDim.x > 1) ? (int)blockIdx.x - 1 : 0;
-  if (panel_cta) qr_factor_panel<T>(Q, sP, spart, sG, sTn, tauv, Tg2, LV, 0, min(QR_PB, n), 0);
+  if (panel_cta) qr_factor_panel<T, QR_RPT>(Q, sP, spart, sG, sTn, tauv, Tg2, LV, 0, min(QR_PB, n), 0);
   __threadfence();
   grid.sync();
   int par = 0;  // parity of the current panel: its T sits in Tg2 + 64 * par
@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(QR_THREADS) k_band_qr_reg(QRMat<T> Q, T* __res
       if (pb1 > 0) qr_apply_cta<T>(Q, sV, sT, sG + 64, sP, LV, k0, k1, pb1, rlast);
       __syncthreads();
       QTICK(2)
-      if (pb1 > 0) qr_factor_panel<T>(Q, sP, spart, sG, sTn, tauv, Tg2 + 64 * (par ^ 1), LV, k1, pb1, staged);
+      if (pb1 > 0) qr_factor_panel<T, QR_RPT>(Q, sP, spart, sG, sTn, tauv, Tg2 + 64 * (par ^ 1), LV, k1, pb1, staged);
       QTICK(3)
     }
     if (!panel_cta || gridDim.x == 1) {
@@ -608,6 +608,130 @@ __global__ void __launch_bounds__(QR_THREADS) k_band_qr_reg(QRMat<T> Q, T* __res
   if (dbg && tid == 0 && blockIdx.x == 0) for (int i = 0; i < 8; ++i) { dbg[i] = tk_[i]; dbg[8 + i] = qr_ftick[i]; qr_ftick[i] = 0; }
 #endif
 #undef QTICK
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tall variant for reduced systems whose columns do not fit the register-resident update (kd + 8 > 640: dense S of
+// the bundled problems with more than 70 cameras). Same structure (panel CTA with look-ahead, compact WY, one grid
+// barrier per panel), but a trailing column is STREAMED twice from L2 in row chunks (w = V^T x, then x -= V z) instead
+// of living in registers, the panel CTA keeps no second panel buffer (the factored panel goes to global memory and
+// is staged like on every other CTA), and the panel factorisation holds RPT rows per thread. The previous
+// fallback (k_band_qr: reflectors applied one by one from global memory, 8 x the L2 traffic, panel factored in
+// global memory between two grid barriers) took 34 ms for 126 cameras and 115 ms for 257.
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__device__ __noinline__ void qr_apply_wy_stream(const T* __restrict__ sV, const T* __restrict__ sT, const int LV, const int k0, const int rlast,
+                                                T* __restrict__ xp0, const int rlo0, T* __restrict__ xp1, const int rlo1, const int lane) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const bool two = xp1 != nullptr;
+  const int nrow = rlast - k0 + 1;   // local rows [0, nrow)
+  T w[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) w[e] = T(0);
+  for (int r = lane; r < nrow; r += 32) {
+    const int i = k0 + r;
+    const T x0 = (i >= rlo0) ? xp0[i] : T(0);
+    const T x1 = (two && i >= rlo1) ? xp1[i] : T(0);
+#pragma unroll
+    for (int c = 0; c < QR_PB; ++c) { const T vv = sV[c * LV + r]; w[c] += vv * x0; w[8 + c] += vv * x1; }
+  }
+  const T mine = warp_reduce_scatter<T, 16, 4>(w, lane);  // lane holds entry (lane >> 1) & 15
+  T z0[QR_PB], z1[QR_PB];
+  {
+    T wt[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) wt[e] = __shfl_sync(FULL, mine, 2 * e);
+#pragma unroll
+    for (int j = 0; j < QR_PB; ++j) {
+      T a0 = T(0), a1 = T(0);
+#pragma unroll
+      for (int i = 0; i < QR_PB; ++i) if (i <= j) { const T tij = sT[i * QR_PB + j]; a0 += tij * wt[i]; a1 += tij * wt[8 + i]; }
+      z0[j] = a0; z1[j] = a1;
+    }
+  }
+  for (int r = lane; r < nrow; r += 32) {
+    const int i = k0 + r;
+    T x0 = (i >= rlo0) ? xp0[i] : T(0);
+    T x1 = (two && i >= rlo1) ? xp1[i] : T(0);
+#pragma unroll
+    for (int c = 0; c < QR_PB; ++c) { const T vv = sV[c * LV + r]; x0 -= vv * z0[c]; x1 -= vv * z1[c]; }
+    if (i >= rlo0) xp0[i] = x0;
+    if (two && i >= rlo1) xp1[i] = x1;
+  }
+}
+
+template <class T>
+struct QrTallSmem {
+  // dynamic layout: sV[QR_PB][LV] | sT[64] | sTn[64] | spart[2][64] | sRow[2][8] | sG[64]
+  static size_t bytes(int kd) { return ((size_t)QR_PB * (kd + QR_PB) + 5 * 64 + 16) * sizeof(T); }
+};
+
+template <class T, int RPT>
+__global__ void __launch_bounds__(QR_THREADS) k_band_qr_tall(QRMat<T> Q, T* __restrict__ tauv, T* __restrict__ rhs, T* __restrict__ Tg2) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char qr_smem_raw[];
+  constexpr int NW = QR_THREADS / 32;
+  const int n = Q.n, kd = Q.kd, ku = Q.ku;
+  const int LV = kd + QR_PB;
+  T* sV = reinterpret_cast<T*>(qr_smem_raw);
+  T* sT = sV + QR_PB * LV;
+  T* sTn = sT + 64;
+  T* spart = sTn + 64;       // [2][64], followed by sRow[2][8]
+  T* sG = spart + 128 + 16;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool panel_cta = blockIdx.x == 0;
+  const int nupd = max(1, (int)gridDim.x - 1);
+  const int ucta = (gridDim.x > 1) ? (int)blockIdx.x - 1 : 0;
+  if (panel_cta) qr_factor_panel<T, RPT>(Q, nullptr, spart, sG, sTn, tauv, Tg2, LV, 0, min(QR_PB, n), 0);
+  __threadfence();
+  grid.sync();
+  int par = 0;
+  for (int k0 = 0; k0 < n; k0 += QR_PB, par ^= 1) {
+    const int pb = min(QR_PB, n - k0);
+    // reflector vectors of this panel -> shared memory (unit diagonal, zeros above and beyond the band), loads batched
+    for (int idx0 = 0; idx0 < QR_PB * LV; idx0 += 8 * QR_THREADS) {
+      T tmp[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = idx0 + tid + QR_THREADS * u, c = idx / LV, r = idx - c * LV, i = k0 + r, j = k0 + c;
+        const bool ld_ = idx < QR_PB * LV && c < pb && r > c && i < n && i <= j + kd;
+        tmp[u] = ld_ ? Q.G[(size_t)j * Q.ld + (r - c + ku)] : ((idx < QR_PB * LV && r == c && c < pb) ? T(1) : T(0));
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int idx = idx0 + tid + QR_THREADS * u; if (idx < QR_PB * LV) sV[idx] = tmp[u]; }
+    }
+    if (tid < 64) sT[tid] = Tg2[64 * par + tid];
+    __syncthreads();
+    const int jlast = min(n - 1, k0 + pb - 1 + ku);
+    const int rlast = min(n - 1, k0 + pb - 1 + kd);
+    const int k1 = k0 + pb, pb1 = min(QR_PB, n - k1);
+    if (panel_cta) {
+      for (int w = 2 * warp; w < pb1; w += 2 * NW) {
+        const int j0 = k1 + w, j1 = j0 + 1;
+        const bool two = w + 1 < pb1;
+        qr_apply_wy_stream<T>(sV, sT, LV, k0, rlast, Q.G + (size_t)j0 * Q.ld + (ku - j0), max(k0, j0 - ku),
+                              two ? Q.G + (size_t)j1 * Q.ld + (ku - j1) : nullptr, max(k0, j1 - ku), lane);
+      }
+      __syncthreads();
+      if (pb1 > 0) qr_factor_panel<T, RPT>(Q, nullptr, spart, sG, sTn, tauv, Tg2 + 64 * (par ^ 1), LV, k1, pb1, 0);
+    }
+    if (!panel_cta || gridDim.x == 1) {
+      const int jfirst = k1 + max(pb1, 0);
+      const int ntrail = max(0, jlast - jfirst + 1);
+      const int nitems = ntrail + 1, ntask = (nitems + 1) / 2;
+      for (int w = ucta * NW + warp; w < ntask; w += nupd * NW) {
+        const int it0 = 2 * w, it1 = 2 * w + 1;
+        const bool rhs0 = it0 == ntrail, has1 = it1 < nitems, rhs1 = it1 == ntrail;
+        const int j0 = jfirst + it0, j1 = jfirst + it1;
+        T* xp0 = rhs0 ? rhs : (Q.G + (size_t)j0 * Q.ld + (ku - j0));
+        T* xp1 = !has1 ? nullptr : (rhs1 ? rhs : (Q.G + (size_t)j1 * Q.ld + (ku - j1)));
+        qr_apply_wy_stream<T>(sV, sT, LV, k0, rlast, xp0, rhs0 ? k0 : max(k0, j0 - ku), xp1, rhs1 ? k0 : max(k0, j1 - ku), lane);
+      }
+    }
+    __threadfence();
+    grid.sync();
+  }
 }
 
 // y = sign * R^-1 (Q^T g): blocked upper-triangular back substitution, single CTA.

@@ -16,12 +16,13 @@ CASES = [(18, 17), (33, 5), (64, 31), (100, 32), (189, 188), (351, 98), (700, 44
 
 
 def band_spd(n, kd, seed):
+    """Random symmetric, strictly diagonally dominant band matrix (half-bandwidth kd) and right-hand side."""
     rng = np.random.default_rng(seed)
-    A = np.zeros((n, n))
-    for d in range(1, kd + 1):
-        v = rng.standard_normal(n - d)
-        A += np.diag(v, -d) + np.diag(v, d)
-    A += np.diag(np.abs(A).sum(axis=1) + rng.uniform(0.5, 2.0, n))
+    A = np.tril(rng.standard_normal((n, n)), -1)
+    i, j = np.indices((n, n), sparse=True)
+    A[(i - j) > kd] = 0.0
+    A = A + A.T
+    A[np.diag_indices(n)] = np.abs(A).sum(axis=1) + rng.uniform(0.5, 2.0, n)
     return A, rng.standard_normal(n)
 
 
@@ -96,19 +97,23 @@ def test_band_solve_float():
     s.close()
 
 
-@pytest.mark.parametrize("n,kd,one_cta", [(800, 700, False), (2313, 300, False), (351, 98, True), (1003, 548, True)])
-def test_band_qr_paths(n, kd, one_cta):
-    """Householder QR of the reduced camera block (QRKIT / MOREQR right block, BAFunctor.h:101,111): the global-memory
-    fallback (kd + 8 > 640), the look-ahead / compact-WY kernel on a larger ragged system (last panel narrower than 8
-    columns), and the single-CTA back substitution next to the cluster one."""
-    if one_cta:
-        os.environ["BA_QR_SOLVE_1CTA"] = "1"
+@pytest.mark.parametrize("n,kd,mode", [(800, 700, ""), (800, 700, "global"), (1134, 1133, ""), (2313, 2312, ""), (2313, 300, ""),
+                                       (351, 98, "one_cta"), (1003, 548, "one_cta")])
+def test_band_qr_paths(n, kd, mode):
+    """Householder QR of the reduced camera block (QRKIT / MOREQR right block, BAFunctor.h:101,111): the tall kernel
+    (kd + 8 > 640: streamed compact-WY updates; dense 126- and 257-camera systems), the global-memory fallback behind
+    it, the look-ahead kernel on a larger ragged system (last panel narrower than 8 columns), and the single-CTA back
+    substitution next to the cluster one."""
+    env = {"global": "BA_QR_GLOBAL", "one_cta": "BA_QR_SOLVE_1CTA"}.get(mode)
+    if env:
+        os.environ[env] = "1"
     try:
         s = _solve("QRKIT", "f64", False)
         A, g = band_spd(n, kd, 500 + n)
         y = s.debug_band_solve(A, g, kd)
     finally:
-        os.environ.pop("BA_QR_SOLVE_1CTA", None)
+        if env:
+            os.environ.pop(env, None)
     ref = np.linalg.solve(A, g)
     assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 1e-12, (n, kd)
     s.close()
