@@ -939,7 +939,7 @@ struct Impl : ba_handle {
 extern "C" {
 
 const char* ba_last_error(void) { return g_err.c_str(); }
-const char* ba_version(void) { return "ba_b200 0.2 (sm_100a; kernels: k_point_factor_warp, k_schur_diag/gather, k_band_ldlt_cluster, k_backsub_eval, k_band_qr)"; }
+const char* ba_version(void) { return "ba_b200 0.3 (sm_100a; kernels: k_point_factor_warp/_big, k_schur_diag/gather, k_band_ldlt_cluster, k_band_qr_reg/_tall, k_backsub_eval/_big)"; }
 
 int ba_create(ba_handle** out, int N, int M, int K, const int* view, const int* point, const double* meas,
               double inlier_threshold, int precision, int variant, int device) {
