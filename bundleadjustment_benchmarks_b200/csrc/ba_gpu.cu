@@ -574,7 +574,7 @@ struct Impl : ba_handle {
     const T diag = (variant == BA_CHOLESKY) ? lamT : sl * sl;  // QR variants square the sqrt(lambda) rows
     mark(0);
     CK(cudaMemsetAsync(d_red.p, 0, (red_count + 2 * (size_t)n) * sizeof(T), stream));
-    if (nunits) { k_point_factor_warp<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, 0, stream>>>(tile_args(lamT), nunits, d_unit_pt.p, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++; }
+    if (nunits) { k_point_factor_warp<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, point_factor_warp_smem_bytes<T>(), stream>>>(tile_args(lamT), nunits, d_unit_pt.p, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++; }
     if (nbig) {
       TileArgs<T> ab = tile_args(lamT); ab.tile_pt = d_big_pt.p;
       k_point_factor<T><<<nbig, TILE, sizeof(TileSmem<T>), stream>>>(ab, 2, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++;

@@ -315,6 +315,12 @@ __device__ __forceinline__ void tile_phases_123(const TileArgs<T>& a, TileSmem<T
 // =============================================================================================
 constexpr int REC = 28;   // scalars per observation record (P and D)
 constexpr int PREC = 16;  // scalars per point record
+// geometry of a record staged in shared memory (see "Staging of records" below)
+template <class T> struct RecGeom {
+  static constexpr int EPC = 16 / (int)sizeof(T);      // scalars per 16-byte chunk
+  static constexpr int CPR = REC / EPC;                // chunks per record (14 / 7)
+  static constexpr int SREC = sizeof(T) == 8 ? 30 : 36;
+};
 
 __device__ __forceinline__ void store4(double* p, double a, double b, double c, double d) {
   *reinterpret_cast<double2*>(p) = make_double2(a, b);
@@ -540,6 +546,7 @@ __device__ __forceinline__ void seg_normal(T (&x)[2][3], const T e0, const T e1,
   seg_sum<T, 3>(cq, s0, n, nmax, i);
 }
 
+template <class T> constexpr size_t point_factor_warp_smem_bytes() { return (size_t)TILE * RecGeom<T>::SREC * sizeof(T); }
 #ifndef BA_PF_MIN_BLOCKS
 #define BA_PF_MIN_BLOCKS 4
 #endif
@@ -586,18 +593,44 @@ __global__ void __launch_bounds__(TILE, BA_PF_MIN_BLOCKS) k_point_factor_warp(Ti
     for (int q = 0; q < 6; ++q) R[q] = Rh[q];
     pm = pmh;
   }
-  if (!act) return;
+  // Records leave through the warp's shared-memory staging area so that the global stores are coalesced: a lane
+  // writing its own 224-byte record touches 32 different lines per store instruction (896 LSU passes per record
+  // type and warp; with both record types that was as long as the whole kernel), two whole records per
+  // instruction (lane = (record, 16-byte chunk)) need 4-5.
+  extern __shared__ __align__(16) unsigned char pfw_smem_raw[];
+  constexpr int EPC = RecGeom<T>::EPC, CPR = RecGeom<T>::CPR, SR = RecGeom<T>::SREC;
+  constexpr int RPI = 32 / CPR, NQ = 32 / RPI;
+  T* const my = reinterpret_cast<T*>(pfw_smem_raw) + (size_t)(threadIdx.x >> 5) * 32 * SR;
+  const int rsub = lane / CPR, part = lane - rsub * CPR;
+  const bool cpl = lane < RPI * CPR;
   T rec[REC];
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
     for (int b = 0; b < 9; ++b) rec[9 * k + b] = x[0][k] * jc[b] + x[1][k] * jc[9 + b];
   rec[27] = T(0);
-  store_rec(Prec + (size_t)o * REC, rec);
+  store_rec(my + lane * SR, rec);
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int r = RPI * q + rsub;
+    if (cpl && r < un)
+      *reinterpret_cast<int4*>(Prec + (size_t)(o0 + r) * REC + part * EPC) = *reinterpret_cast<const int4*>(my + r * SR + part * EPC);
+  }
+  __syncwarp();
 #pragma unroll
   for (int b = 0; b < 18; ++b) rec[b] = jc[b];
   fill_drec_tail<T>(rec, x[0][0], x[0][1], x[0][2], x[1][0], x[1][1], x[1][2], cq[0], cq[1], cq[2], e0, e1);
-  store_rec(Drec + sl * REC, rec);
+  store_rec(my + lane * SR, rec);
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int r = RPI * q + rsub;
+    const size_t slr = (size_t)__shfl_sync(FULL, (int)sl, r & 31);
+    if (cpl && r < un)
+      *reinterpret_cast<int4*>(Drec + slr * REC + part * EPC) = *reinterpret_cast<const int4*>(my + r * SR + part * EPC);
+  }
+  if (!act) return;
   if (i == 0) {
     T* q = Ptrec + (size_t)pj * PREC;
     store4(q, R[0], R[1], R[2], R[3]);
@@ -612,11 +645,6 @@ __global__ void __launch_bounds__(TILE, BA_PF_MIN_BLOCKS) k_point_factor_warp(Ti
 // shared-memory slot of SREC scalars: 8 consecutive lanes reading 16 bytes each at that stride hit 32
 // different banks (30 doubles = 60 words = 28 mod 32; 36 floats = 4 mod 32).
 // ---------------------------------------------------------------------------------------------
-template <class T> struct RecGeom {
-  static constexpr int EPC = 16 / (int)sizeof(T);      // scalars per 16-byte chunk
-  static constexpr int CPR = REC / EPC;                // chunks per record (14 / 7)
-  static constexpr int SREC = sizeof(T) == 8 ? 30 : 36;
-};
 __device__ __forceinline__ void rec_cp16(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
