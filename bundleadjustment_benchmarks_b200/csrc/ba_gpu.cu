@@ -217,7 +217,7 @@ struct Impl : ba_handle {
   DevBuf<int> d_view, d_point, d_pt_start, d_tile_pt, d_info;
   DevBuf<int> d_slot, d_cam_start, d_blk_a, d_blk_b, d_blk_start, d_counter;  // static structure of the deterministic Schur gather
   DevBuf<int2> d_pairs;
-  DevBuf<int> d_unit_pt, d_big_pt, d_huge_pt;  // warp units (points with <= 32 observations) / tiles of the larger points / points with > TILE observations
+  DevBuf<int> d_seg, d_unit_pt, d_big_pt, d_huge_pt;  // warp units (points with <= 32 observations) / tiles of the larger points / points with > TILE observations
   int nunits = 0, nbig = 0, nhuge = 0, huge_max = 0;
   DevBuf<T> d_P, d_D, d_Pt;  // per-observation (P, D) / per-point records written by k_point_factor*
   int nblocks = 0, gather_grid = 0;
@@ -317,7 +317,7 @@ struct Impl : ba_handle {
       if (nj > 32) { big_pt.push_back(j); big_pt.push_back(j + 1); ++j; continue; }
       int j1 = j, cnt = 0;
       while (j1 < M && pt_start[j1 + 1] - pt_start[j1] <= 32 && cnt + (pt_start[j1 + 1] - pt_start[j1]) <= 32) { cnt += pt_start[j1 + 1] - pt_start[j1]; ++j1; }
-      unit_pt.push_back(j); unit_pt.push_back(j1);
+      unit_pt.push_back(pt_start[j]); unit_pt.push_back(cnt);  // (first observation, observation count) of the unit
       j = j1;
     }
     nunits = (int)unit_pt.size() / 2; nbig = (int)big_pt.size() / 2;
@@ -389,6 +389,15 @@ struct Impl : ba_handle {
     CK(d_pairs.alloc(pairs.size()));
     CK(d_P.alloc((size_t)K * REC)); CK(d_D.alloc((size_t)K * REC)); CK(d_Pt.alloc((size_t)M * PREC));
     CK(cudaMemcpyAsync(d_slot.p, slot.data(), K * sizeof(int), cudaMemcpyHostToDevice, stream));
+    {
+      std::vector<int> seg(K);   // per observation: index within its point | min(count, 255) << 8 (warp units: count <= 32)
+      for (int j = 0; j < M; ++j) {
+        const int nj = pt_start[j + 1] - pt_start[j];
+        for (int q = 0; q < nj; ++q) seg[pt_start[j] + q] = std::min(q, 255) | (std::min(nj, 255) << 8);
+      }
+      CK(d_seg.alloc(K));
+      CK(cudaMemcpy(d_seg.p, seg.data(), K * sizeof(int), cudaMemcpyHostToDevice));
+    }
     CK(cudaMemcpyAsync(d_cam_start.p, cam_start.data(), (N + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_blk_a.p, blk_a.data(), nblocks * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_blk_b.p, blk_b.data(), nblocks * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -574,7 +583,7 @@ struct Impl : ba_handle {
     const T diag = (variant == BA_CHOLESKY) ? lamT : sl * sl;  // QR variants square the sqrt(lambda) rows
     mark(0);
     CK(cudaMemsetAsync(d_red.p, 0, (red_count + 2 * (size_t)n) * sizeof(T), stream));
-    if (nunits) { k_point_factor_warp<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, point_factor_warp_smem_bytes<T>(), stream>>>(tile_args(lamT), nunits, d_unit_pt.p, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++; }
+    if (nunits) { k_point_factor_warp<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, point_factor_warp_smem_bytes<T>(), stream>>>(tile_args(lamT), nunits, d_unit_pt.p, d_seg.p, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++; }
     if (nbig) {
       TileArgs<T> ab = tile_args(lamT); ab.tile_pt = d_big_pt.p;
       k_point_factor<T><<<nbig, TILE, sizeof(TileSmem<T>), stream>>>(ab, 2, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++;

@@ -551,20 +551,21 @@ template <class T> constexpr size_t point_factor_warp_smem_bytes() { return (siz
 #define BA_PF_MIN_BLOCKS 4
 #endif
 template <class T>
-__global__ void __launch_bounds__(TILE, BA_PF_MIN_BLOCKS) k_point_factor_warp(TileArgs<T> a, int nunits, const int* __restrict__ unit_pt, const int* __restrict__ slot,
+__global__ void __launch_bounds__(TILE, BA_PF_MIN_BLOCKS) k_point_factor_warp(TileArgs<T> a, int nunits, const int* __restrict__ unit_obs, const int* __restrict__ seg, const int* __restrict__ slot,
                                                             T* __restrict__ Prec, T* __restrict__ Drec, T* __restrict__ Ptrec) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, u = blockIdx.x * (TILE / 32) + (threadIdx.x >> 5);
   if (u >= nunits) return;
-  const int p0 = __ldg(unit_pt + 2 * u), p1 = __ldg(unit_pt + 2 * u + 1);
-  const int o0 = __ldg(a.pt_start + p0), un = __ldg(a.pt_start + p1) - o0;
+  // three levels of dependent loads (unit -> per-observation indices -> camera / point), not five: the unit table
+  // holds (first observation, count) and `seg` holds each observation's (index within its point | count << 8)
+  const int2 uo = __ldg(reinterpret_cast<const int2*>(unit_obs) + u);
+  const int o0 = uo.x, un = uo.y;
   const bool act = lane < un;
   const int o = o0 + (act ? lane : 0);
-  const int cam_idx = __ldg(a.view + o), pj = __ldg(a.point + o);
+  const int cam_idx = __ldg(a.view + o), pj = __ldg(a.point + o), sg = __ldg(seg + o);
   const size_t sl = (size_t)__ldg(slot + o);   // consumed at the very end: issued with the first level of loads
-  int s0 = lane, n = 1;
-  if (act) { const int ps = __ldg(a.pt_start + pj); s0 = ps - o0; n = __ldg(a.pt_start + pj + 1) - ps; }
-  const int i = lane - s0;
+  const int i = act ? (sg & 0xff) : 0, n = act ? (sg >> 8) : 1;
+  const int s0 = lane - i;
   Cam<T> c; load_cam<T>(a.cams, cam_idx, c);
   const T X0 = __ldg(a.X + 3 * (size_t)pj), X1 = __ldg(a.X + 3 * (size_t)pj + 1), X2 = __ldg(a.X + 3 * (size_t)pj + 2);
   const T m0 = __ldg(a.meas + 2 * (size_t)o), m1 = __ldg(a.meas + 2 * (size_t)o + 1);
