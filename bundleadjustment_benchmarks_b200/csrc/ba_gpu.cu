@@ -290,12 +290,15 @@ struct Impl : ba_handle {
     }
     bw = 0;
     for (int j = 0; j < M; ++j) bw = std::max(bw, view[pt_start[j + 1] - 1] - view[pt_start[j]]);
-    // back-substitution tiles: (first, end) pairs of consecutive points whose observations fit TILE lanes; a point
+    // back-substitution tiles: (first point, end point, first observation, observations) of consecutive points whose
+    // observations fit TILE lanes; a point
     // with more than TILE observations ("huge": long tracks of real BAL files) gets its own CTA in separate kernels
     std::vector<int> tile_pt, huge_pt;
     {
       int first = 0, cur_obs = 0, cur_pts = 0;
-      auto close = [&](int end) { if (end > first) { tile_pt.push_back(first); tile_pt.push_back(end); } };
+      auto close = [&](int end) {
+        if (end > first) { tile_pt.push_back(first); tile_pt.push_back(end); tile_pt.push_back(pt_start[first]); tile_pt.push_back(pt_start[end] - pt_start[first]); }
+      };
       for (int j = 0; j < M; ++j) {
         const int nj = pt_start[j + 1] - pt_start[j];
         if (nj > TILE) { close(j); huge_pt.push_back(j); first = j + 1; cur_obs = 0; cur_pts = 0; continue; }
@@ -306,7 +309,7 @@ struct Impl : ba_handle {
     }
     nhuge = (int)huge_pt.size();
     for (int j : huge_pt) huge_max = std::max(huge_max, pt_start[j + 1] - pt_start[j]);
-    ntiles = (int)tile_pt.size() / 2;
+    ntiles = (int)tile_pt.size() / 4;
 
     // point factor work units: one warp per run of consecutive points whose observations fit 32 lanes
     // (k_point_factor_warp); a point with more than 32 observations becomes its own shared-memory tile
@@ -365,7 +368,7 @@ struct Impl : ba_handle {
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) CK(cudaEventCreate(&e));
-    CK(d_view.alloc(K)); CK(d_point.alloc(K)); CK(d_pt_start.alloc(M + 1)); CK(d_tile_pt.alloc(2 * (size_t)ntiles + 2)); CK(d_huge_pt.alloc(nhuge + 1)); CK(d_info.alloc(1));
+    CK(d_view.alloc(K)); CK(d_point.alloc(K)); CK(d_pt_start.alloc(M + 1)); CK(d_tile_pt.alloc(4 * (size_t)ntiles + 4)); CK(d_huge_pt.alloc(nhuge + 1)); CK(d_info.alloc(1));
     CK(d_meas.alloc(2 * (size_t)K));
     CK(d_cams.alloc((size_t)N * CAM_STRIDE)); CK(d_cams_test.alloc((size_t)N * CAM_STRIDE));
     CK(d_X.alloc(3 * (size_t)M)); CK(d_X_test.alloc(3 * (size_t)M));

@@ -958,8 +958,8 @@ __global__ void __launch_bounds__(TILE, 5) k_backsub_eval(TileArgs<T> a, const T
   __shared__ T sx[3][TP];
   __shared__ double red[3 * (TILE / 32)];
   const int t = threadIdx.x, tile = blockIdx.x, lane = t & 31, w0 = t & ~31;
-  const int p0 = __ldg(a.tile_pt + 2 * tile), p1 = __ldg(a.tile_pt + 2 * tile + 1), npts = p1 - p0;  // (first, end) pairs
-  const int o0 = __ldg(a.pt_start + p0), nobs = __ldg(a.pt_start + p1) - o0;
+  const int4 ti = __ldg(reinterpret_cast<const int4*>(a.tile_pt) + tile);  // (first point, end point, first observation, observations)
+  const int p0 = ti.x, p1 = ti.y, npts = p1 - p0, o0 = ti.z, nobs = ti.w;
   // Every warp stages the records and dx_cam rows of ITS 32 observations (lane = (record, chunk): one copy
   // instruction moves RPI whole records; the tile's records are contiguous), so a __syncwarp suffices before
   // they are read. Every load that does not depend on staged data is issued before the wait: the kernel is a
