@@ -676,7 +676,10 @@ template <int LO, int HI> __device__ __forceinline__ void lds_rec(const float* s
 // At the end of a block the 32 lane accumulators are summed in lane order through shared memory (fixed
 // order -> bit-reproducible) and lanes 0..26 write the block.
 // ---------------------------------------------------------------------------------------------
-constexpr int GATHER_WARPS = 6;
+#ifndef BA_GATHER_WARPS
+#define BA_GATHER_WARPS 7
+#endif
+constexpr int GATHER_WARPS = BA_GATHER_WARPS;
 constexpr int GATHER_THREADS = 32 * GATHER_WARPS;
 template <class T> constexpr size_t gather_rec_bytes() { return (size_t)GATHER_WARPS * 2 * 64 * RecGeom<T>::SREC * sizeof(T); }
 template <class T> constexpr size_t gather_smem_bytes() { return gather_rec_bytes<T>() + (size_t)GATHER_WARPS * 2 * 32 * sizeof(int2); }
