@@ -948,7 +948,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_schur_diag(const int* __res
 template <class T> constexpr size_t backsub_smem_bytes() { return (size_t)TILE * (RecGeom<T>::SREC + 9) * sizeof(T); }
 
 template <class T>
-__global__ void __launch_bounds__(TILE, 5) k_backsub_eval(TileArgs<T> a, const T* __restrict__ Prec,
+__global__ void __launch_bounds__(TILE, 4) k_backsub_eval(TileArgs<T> a, const T* __restrict__ Prec,
                                                           const T* __restrict__ Ptrec, const T* __restrict__ dx_cam, const T* __restrict__ cams_test,
                                                           T* __restrict__ dx_pt, T* __restrict__ X_test, double* __restrict__ partials, int ntiles) {
   constexpr unsigned FULL = 0xffffffffu;
