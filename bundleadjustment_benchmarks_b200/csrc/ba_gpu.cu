@@ -68,7 +68,7 @@ NcclApi g_nccl;
 // ------------------------------------------------------------------------------- small kernels
 using namespace ba;
 
-// mode 0: energy partials; 1: + residuals out; 2: Jacobian blocks out; 3: column-norm accumulation
+// mode 0: energy partials; 1: + residuals out; 2: Jacobian blocks out (column norms: k_colnorm_pt / k_colnorm_cam below)
 template <class T, int MODE>
 __global__ void __launch_bounds__(256) k_obs(int K, const int* __restrict__ view, const int* __restrict__ point, const T* __restrict__ meas,
                                              const T* __restrict__ cams, const T* __restrict__ X, T tau2, int M,
@@ -93,11 +93,6 @@ __global__ void __launch_bounds__(256) k_obs(int K, const int* __restrict__ view
         for (int k = 0; k < 18; ++k) out0[18 * (size_t)i + k] = jc[k];
 #pragma unroll
         for (int k = 0; k < 6; ++k) out1[6 * (size_t)i + k] = jp[k];
-      } else {
-#pragma unroll
-        for (int b = 0; b < 3; ++b) atomicAdd(out0 + 3 * (size_t)pj + b, jp[b] * jp[b] + jp[3 + b] * jp[3 + b]);
-#pragma unroll
-        for (int b = 0; b < 9; ++b) atomicAdd(out0 + 3 * (size_t)M + 9 * (size_t)cidx + b, jc[b] * jc[b] + jc[9 + b] * jc[9 + b]);
       }
     }
     acc = (double)(e0 * e0 + e1 * e1);
@@ -111,6 +106,53 @@ __global__ void __launch_bounds__(256) k_obs(int K, const int* __restrict__ view
     for (int w = 0; w < 8; ++w) s += sred[w];
     partials[blockIdx.x] = s;
   }
+}
+
+// Squared column norms of J (QRChol.h:267-280), without atomics so that lambda_0 - and with it a whole LM run - is
+// bit-reproducible: one thread per point walks the point's (contiguous) observations, one CTA per camera walks the
+// camera's camera-major slots; fixed summation order in both.
+template <class T>
+__global__ void __launch_bounds__(256) k_colnorm_pt(int M, const int* __restrict__ pt_start, const int* __restrict__ view, const T* __restrict__ meas,
+                                                    const T* __restrict__ cams, const T* __restrict__ X, T tau2, T* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const T X0 = __ldg(X + 3 * (size_t)j), X1 = __ldg(X + 3 * (size_t)j + 1), X2 = __ldg(X + 3 * (size_t)j + 2);
+  T s0 = T(0), s1 = T(0), s2 = T(0);
+  for (int i = __ldg(pt_start + j); i < __ldg(pt_start + j + 1); ++i) {
+    Cam<T> c; load_cam<T>(cams, __ldg(view + i), c);
+    T e0, e1, jc[18], jp[6];
+    obs_jacobian<T>(c, X0, X1, X2, __ldg(meas + 2 * (size_t)i), __ldg(meas + 2 * (size_t)i + 1), tau2, e0, e1, jc, jp);
+    s0 += jp[0] * jp[0] + jp[3] * jp[3]; s1 += jp[1] * jp[1] + jp[4] * jp[4]; s2 += jp[2] * jp[2] + jp[5] * jp[5];
+  }
+  out[3 * (size_t)j] = s0; out[3 * (size_t)j + 1] = s1; out[3 * (size_t)j + 2] = s2;
+}
+
+template <class T>
+__global__ void __launch_bounds__(128) k_colnorm_cam(const int* __restrict__ cam_start, const int* __restrict__ obs_of_slot, const int* __restrict__ point,
+                                                     const T* __restrict__ meas, const T* __restrict__ cams, const T* __restrict__ X, T tau2,
+                                                     T* __restrict__ out /* 9 per camera */) {
+  __shared__ T part[4][9];
+  const int cam = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Cam<T> c; load_cam<T>(cams, cam, c);
+  T s[9];
+#pragma unroll
+  for (int b = 0; b < 9; ++b) s[b] = T(0);
+  for (int q = __ldg(cam_start + cam) + threadIdx.x; q < __ldg(cam_start + cam + 1); q += 128) {
+    const int i = __ldg(obs_of_slot + q), pj = __ldg(point + i);
+    T e0, e1, jc[18], jp[6];
+    obs_jacobian<T>(c, __ldg(X + 3 * (size_t)pj), __ldg(X + 3 * (size_t)pj + 1), __ldg(X + 3 * (size_t)pj + 2), __ldg(meas + 2 * (size_t)i),
+                    __ldg(meas + 2 * (size_t)i + 1), tau2, e0, e1, jc, jp);
+#pragma unroll
+    for (int b = 0; b < 9; ++b) s[b] += jc[b] * jc[b] + jc[9 + b] * jc[9 + b];
+  }
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s[b] += __shfl_down_sync(0xffffffffu, s[b], off);
+    if (lane == 0) part[warp][b] = s[b];
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) out[9 * (size_t)cam + threadIdx.x] = ((part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x]) + part[3][threadIdx.x];
 }
 
 // deterministic final reduction: block b sums partials[b*count .. (b+1)*count) -> out[b]
@@ -217,7 +259,7 @@ struct Impl : ba_handle {
   DevBuf<int> d_view, d_point, d_pt_start, d_tile_pt, d_info;
   DevBuf<int> d_slot, d_cam_start, d_blk_a, d_blk_b, d_blk_start, d_counter;  // static structure of the deterministic Schur gather
   DevBuf<int2> d_pairs;
-  DevBuf<int> d_seg, d_unit_pt, d_big_pt, d_huge_pt;  // warp units (points with <= 32 observations) / tiles of the larger points / points with > TILE observations
+  DevBuf<int> d_seg, d_obs_of_slot, d_unit_pt, d_big_pt, d_huge_pt;  // warp units (points with <= 32 observations) / tiles of the larger points / points with > TILE observations
   int nunits = 0, nbig = 0, nhuge = 0, huge_max = 0;
   DevBuf<T> d_P, d_D, d_Pt;  // per-observation (P, D) / per-point records written by k_point_factor*
   int nblocks = 0, gather_grid = 0;
@@ -393,6 +435,12 @@ struct Impl : ba_handle {
     CK(d_P.alloc((size_t)K * REC)); CK(d_D.alloc((size_t)K * REC)); CK(d_Pt.alloc((size_t)M * PREC));
     CK(cudaMemcpyAsync(d_slot.p, slot.data(), K * sizeof(int), cudaMemcpyHostToDevice, stream));
     {
+      std::vector<int> inv(K);   // observation stored at each camera-major slot (column norms of the camera columns)
+      for (int i = 0; i < K; ++i) inv[slot[i]] = i;
+      CK(d_obs_of_slot.alloc(K));
+      CK(cudaMemcpy(d_obs_of_slot.p, inv.data(), K * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    {
       std::vector<int> seg(K);   // per observation: index within its point | min(count, 255) << 8 (warp units: count <= 32)
       for (int j = 0; j < M; ++j) {
         const int nj = pt_start[j + 1] - pt_start[j];
@@ -551,10 +599,11 @@ struct Impl : ba_handle {
     if (max_cn2 || max_cn) {
       const size_t np = 3 * (size_t)M + 9 * (size_t)N;
       if (d_tmp.n < np) CK(d_tmp.alloc(np));
-      CK(cudaMemsetAsync(d_tmp.p, 0, np * sizeof(T), stream));
-      k_obs<T, 3><<<nb, 256, 0, stream>>>(K, d_view.p, d_point.p, d_meas.p, d_cams.p, d_X.p, tau2, M, d_partials.p, d_tmp.p, nullptr);
+      k_obs<T, 0><<<nb, 256, 0, stream>>>(K, d_view.p, d_point.p, d_meas.p, d_cams.p, d_X.p, tau2, M, d_partials.p, nullptr, nullptr);
       k_reduce<<<1, 256, 0, stream>>>(d_partials.p, nb, d_scal.p + 0);
-      launches += 2;
+      k_colnorm_pt<T><<<(M + 255) / 256, 256, 0, stream>>>(M, d_pt_start.p, d_view.p, d_meas.p, d_cams.p, d_X.p, tau2, d_tmp.p);
+      k_colnorm_cam<T><<<N, 128, 0, stream>>>(d_cam_start.p, d_obs_of_slot.p, d_point.p, d_meas.p, d_cams.p, d_X.p, tau2, d_tmp.p + 3 * (size_t)M);
+      launches += 4;
       if (comm) {  // camera column norms are sums over all ranks' observations
         NK(g_nccl.AllReduce(d_tmp.p + 3 * (size_t)M, d_tmp.p + 3 * (size_t)M, 9 * (size_t)N, nccl_t(), ncclSum, comm, stream));
       }

@@ -235,6 +235,21 @@ def test_edge_cases_gpu():
         solver.GpuSolver(bad, "QRCHOL")
 
 
+def test_lambda0_inputs_bit_reproducible():
+    """lambda_0 = 1e-12 max_c |J(:,c)|^2 (QRChol.h:267-280) starts every LM run: the column norms are accumulated
+    without atomics, so two handles return bit-identical values (and hence bit-identical LM trajectories)."""
+    p = bal.load_named("problem-39-18060")
+    vals = []
+    for _ in range(2):
+        s = solver.GpuSolver(p, "QRCHOL")
+        vals.append(s.linearize())
+        s.close()
+    assert vals[0] == vals[1]
+    o = Oracle(p)
+    eo, cn2o, cno = o.linearize()
+    assert relv(vals[0][0], eo) < 1e-12 and relv(vals[0][1], cn2o) < 1e-12 and relv(vals[0][2], cno) < 1e-12
+
+
 def _long_track_problem():
     """320 cameras; 300 ordinary points (2-12 observations), 30 points with 33-128 and 10 points with 150-319
     observations (long tracks of real BAL files): the three point-factor paths in one problem. The three sets share
