@@ -23,7 +23,7 @@ SYMBOLS = [
     "ba_compute", "ba_solve_try", "ba_accept", "ba_reject", "ba_get_dx", "ba_get_residuals",
     "ba_get_reduced_system", "ba_keep_reduced_system", "ba_get_jacobian", "ba_launch_count",
     "ba_stage_ms", "ba_set_profiling", "ba_timer_start", "ba_timer_stop", "ba_debug_counters",
-    "ba_debug_band_solve",
+    "ba_debug_band_solve", "ba_numeric_status", "ba_set_strict_numeric",
 ]
 
 _LIB = None
@@ -52,7 +52,7 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(SO_PATH):
+    if needs_build():  # missing, or older than any source: never measure a stale binary
         build()
     L = C.CDLL(SO_PATH)  # raises OSError loudly if the CUDA extension is missing/unloadable
     dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
@@ -83,6 +83,8 @@ def lib():
     L.ba_debug_counters.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.ba_debug_band_solve.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp]
     L.ba_timer_start.argtypes = [vp]
+    L.ba_numeric_status.argtypes = [vp, ip]
+    L.ba_set_strict_numeric.argtypes = [vp, C.c_int]
     L.ba_timer_stop.argtypes = [vp, dp]
     for s in SYMBOLS:
         if s not in ("ba_last_error", "ba_version"):

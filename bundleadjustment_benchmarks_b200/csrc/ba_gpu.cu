@@ -1,12 +1,12 @@
 // libba_b200.so — C ABI (include/ba_gpu.h) over hand-written sm_100a kernels. No CPU fallback.
 // Host orchestration of one LM trial:
-//   ba_compute : init S | k_schur (Jacobian + point block factor + Schur accumulation) | all-reduce | factor
+//   ba_compute : init S | k_point_factor_warp (Jacobian + point block factor -> P/D/point records) | k_schur_diag +
+//                k_schur_gather (reduced camera system from the records, no atomics) | all-reduce | factor
 //   ba_solve_try: reduced solve | camera update | k_backsub_eval (back-substitution + update + test energy) | reduce
 // Reference call sites replaced: src/Eigen_ext/BacktrackLevMarqQRChol.h:257-371 (and the MOREQR /
 // CHOLESKY counterparts), src/Optimization/BAFunctor.{h,cpp}.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
-#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -38,6 +38,17 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // ------------------------------------------------------------------------------------------ NCCL
+// libnccl.so.2 is dlopen'ed and nccl.h is not needed to build: the handful of ABI-stable types and enum values
+// used here (nccl.h of NCCL 2.x: ncclUniqueId = 128 opaque bytes; ncclSuccess = 0; ncclSum = 0, ncclMax = 2;
+// ncclFloat = 7, ncclDouble = 8) are declared locally.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+typedef int ncclDataType_t;
+typedef int ncclRedOp_t;
+constexpr ncclResult_t ncclSuccess = 0;
+constexpr ncclRedOp_t ncclSum = 0, ncclMax = 2, ncclMin = 3;
+constexpr ncclDataType_t ncclInt = 2, ncclFloat = 7, ncclDouble = 8;
 struct NcclApi {
   void* lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -237,6 +248,8 @@ struct ba_handle {
   virtual int debug_counters(long long*) = 0;
   virtual int debug_band_solve(int, int, const double*, const double*, double*) = 0;
   int bw = 0;
+  int numeric_info = 0;        // last ba_solve_try: 0 ok, > 0 zero/NaN pivot at that (1-based) row of the reduced system, -1 non-finite step
+  bool strict_numeric = false; // ba_set_strict_numeric: return BA_ERR_NUMERIC instead of reporting a NaN test energy
   bool keep_reduced = false;
   bool force_grid_ldlt = false;
   bool profiling = false;
@@ -278,7 +291,7 @@ struct Impl : ba_handle {
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
-  int coop_grid = 0, coop_grid_qr = 0;
+  int coop_grid = 0, coop_grid_qr = 0, sm_count = 148;
 
   ~Impl() override {
     cudaSetDevice(device);
@@ -465,6 +478,7 @@ struct Impl : ba_handle {
     CK(cudaFuncSetAttribute(k_point_factor<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<T>)));
     int occ = 0, sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    sm_count = sms;
     CK(cudaFuncSetAttribute(k_schur_gather<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gather_smem_bytes<T>()));
     CK(cudaFuncSetAttribute(k_schur_diag<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem_bytes<T>()));
     CK(cudaFuncSetAttribute(k_backsub_eval<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)backsub_smem_bytes<T>()));
@@ -711,7 +725,7 @@ struct Impl : ba_handle {
           T* Rv = d_rev.p + ldsv; T* gr = d_rev.p + rev_count;
           BandMat<T> Ar{Rv, lds(), np, kd};
           BandMat<T> Am{Sv() + (size_t)r0 * ldsv + r0, lds(), nm, std::min(kd, nm - 1)};
-          const int ab = 4 * 148;
+          const int ab = 4 * sm_count;
           k_band_reverse<T><<<ab, 256, 0, stream>>>(A, gvec(), Rv, gr, np, q * NB);
           LdltJob<T> job = {};
           job.sign = T(-1);
@@ -854,6 +868,20 @@ struct Impl : ba_handle {
     if (rho_den) *rho_den = lambda * dx2 - h_scal[3] - h_scal[6];  // dx^T(lambda dx + JtRes), JtRes = -J^T r
     if (energy_test) *energy_test = h_scal[1];
     tried = true;
+    // A singular / NaN reduced system (zero or NaN pivot recorded by the LDL^T kernels, or a non-finite step out of
+    // either right-block solver) is never reported as an ordinary trial: the test energy becomes NaN, which the
+    // reference's `energyTest < m_energy` (QRChol.h:374) treats as a rejection, and ba_numeric_status says why;
+    // with ba_set_strict_numeric the call fails with BA_ERR_NUMERIC instead.
+    int bad = 0;
+    std::memcpy(&bad, h_scal + 8, sizeof(int));
+    numeric_info = bad > 0 ? bad : ((std::isfinite(dx2) && std::isfinite(h_scal[1])) ? 0 : -1);
+    if (numeric_info != 0) {
+      if (energy_test) *energy_test = std::nan("");
+      if (strict_numeric) {
+        if (numeric_info > 0) return fail(BA_ERR_NUMERIC, "reduced camera system: zero or NaN pivot at row %d (lambda = %g)", numeric_info - 1, lambda);
+        return fail(BA_ERR_NUMERIC, "non-finite step from the reduced camera system (lambda = %g)", lambda);
+      }
+    }
     return BA_OK;
   }
 
@@ -931,6 +959,16 @@ struct Impl : ba_handle {
     std::memcpy(&id, id128, sizeof(id));
     rank = rank_; nranks = nranks_;
     NK(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    // every rank must use the same band layout (the all-reduce of [S | g | gJ] is element-wise): take the largest
+    // block half-bandwidth over the ranks, whatever ba_set_bandwidth was or was not called with
+    int* dbw = reinterpret_cast<int*>(d_dbg.p);
+    CK(cudaMemcpyAsync(dbw, &bw, sizeof(int), cudaMemcpyHostToDevice, stream));
+    NK(g_nccl.AllReduce(dbw, dbw, 1, ncclInt, ncclMax, comm, stream));
+    int bw_all = bw;
+    CK(cudaMemcpyAsync(&bw_all, dbw, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaMemsetAsync(d_dbg.p, 0, sizeof(long long), stream));
+    if (bw_all != bw) { bw = std::min(bw_all, N - 1); computed = tried = false; return alloc_reduced(); }
     return BA_OK;
   }
 
@@ -1045,5 +1083,7 @@ int ba_debug_counters(ba_handle* h, long long* out16) { H_CHECK; return h->debug
 int ba_timer_start(ba_handle* h) { H_CHECK; return h->timer_start(); }
 int ba_debug_band_solve(ba_handle* h, int n, int kd, const double* S, const double* g, double* y) { H_CHECK; return h->debug_band_solve(n, kd, S, g, y); }
 int ba_timer_stop(ba_handle* h, double* ms) { H_CHECK; return h->timer_stop(ms); }
+int ba_numeric_status(ba_handle* h, int* info) { H_CHECK; if (info) *info = h->numeric_info; return BA_OK; }
+int ba_set_strict_numeric(ba_handle* h, int enable) { H_CHECK; h->strict_numeric = enable != 0; return BA_OK; }
 
 }  // extern "C"

@@ -10,12 +10,12 @@
 //   back-substitution + colsPermutation                    QRChol.h:344-360
 //   increment_in_place + functor(xTest)                    QRChol.h:363-371, BAFunctor.h:299-342
 //
-// Work decomposition (B200-first): a CTA owns a TILE of consecutive points whose
-// observations fit TILE lanes. Phase 1 is one lane per OBSERVATION (full-lane Jacobians), phase 2
-// one lane per POINT (3-column Householder QR with column pivoting, thin Q formed in place in
-// shared memory), phase 3 one lane per observation (R12_i = Q1_i^T Jc_i), phase 4 one WARP per
-// camera pair of a point with lanes <-> the 81 entries of the 9x9 block, so that the atomics into
-// the reduced camera matrix are coalesced 72-byte row segments.
+// Work decomposition (B200-first): k_point_factor_warp gives one WARP a unit of consecutive
+// points whose observations fit 32 lanes (lane = observation, everything in registers, segmented shuffles);
+// the tile kernel k_point_factor (a CTA owns consecutive points whose observations fit TILE lanes: phase 1 one
+// lane per OBSERVATION, phase 2 one lane per POINT, phase 3 one lane per observation) only serves points with
+// 33..128 observations, k_point_factor_big the longer tracks. All of them write per-observation records; the
+// reduced camera matrix is then WRITTEN (no atomics) by k_schur_diag / k_schur_gather from static pair lists.
 #pragma once
 #include "ba_model.cuh"
 
@@ -199,9 +199,12 @@ __device__ void point_normal(S& sm, int p, int lo, int n, T lambda) {
     g0 += a0 * e0 + b0 * e1; g1 += a1 * e0 + b1 * e1; g2 += a2 * e0 + b2 * e1;
   }
   sm.G[p] = g0; sm.G[sm.ostride() + p] = g1; sm.G[2 * sm.ostride() + p] = g2;
+  // V = Jp^T Jp + lambda I has no eigenvalue below lambda, hence no exact pivot below lambda either: the floor only
+  // acts when cancellation (low-parallax points, float) has driven a computed pivot to or below zero, and keeps the
+  // square roots below finite (the reference's SimplicialLDLT never takes the root of a pivot)
   const T d0 = v00, l10 = v10 / d0, l20 = v20 / d0;
-  const T d1 = v11 - l10 * l10 * d0, l21 = (v21 - l20 * l10 * d0) / d1;
-  const T d2 = v22 - l20 * l20 * d0 - l21 * l21 * d1;
+  const T d1 = tmax(v11 - l10 * l10 * d0, lambda), l21 = (v21 - l20 * l10 * d0) / d1;
+  const T d2 = tmax(v22 - l20 * l20 * d0 - l21 * l21 * d1, lambda);
   const T s0 = tsqrt(d0), s1 = tsqrt(d1), s2 = tsqrt(d2);
   const T r00 = s0, r01 = s0 * l10, r02 = s0 * l20, r11 = s1, r12 = s1 * l21, r22 = s2;
   sm.Rm[0 * sm.ostride() + p] = r00; sm.Rm[1 * sm.ostride() + p] = r01; sm.Rm[2 * sm.ostride() + p] = r02;
@@ -529,8 +532,8 @@ __device__ __forceinline__ void seg_normal(T (&x)[2][3], const T e0, const T e1,
   seg_sum<T, 6>(v, s0, n, nmax, i);
   const T v00 = v[0] + lambda, v10 = v[1], v11 = v[2] + lambda, v20 = v[3], v21 = v[4], v22 = v[5] + lambda;
   const T d0 = v00, l10 = v10 / d0, l20 = v20 / d0;
-  const T d1 = v11 - l10 * l10 * d0, l21 = (v21 - l20 * l10 * d0) / d1;
-  const T d2 = v22 - l20 * l20 * d0 - l21 * l21 * d1;
+  const T d1 = tmax(v11 - l10 * l10 * d0, lambda), l21 = (v21 - l20 * l10 * d0) / d1;  // pivot floor: see point_normal
+  const T d2 = tmax(v22 - l20 * l20 * d0 - l21 * l21 * d1, lambda);
   const T q0 = tsqrt(d0), q1 = tsqrt(d1), q2 = tsqrt(d2);
   R[0] = q0; R[1] = q0 * l10; R[2] = q0 * l20; R[3] = q1; R[4] = q1 * l21; R[5] = q2;
   pm = 0 | (1 << 2) | (2 << 4);

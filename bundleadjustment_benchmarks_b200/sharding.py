@@ -17,6 +17,8 @@ from .bal import BALProblem
 
 
 def point_ranges(prob: BALProblem, nranks: int) -> List[Tuple[int, int]]:
+    if nranks < 1 or prob.M < nranks:
+        raise ValueError(f"cannot shard {prob.M} points over {nranks} ranks: every rank needs at least one point")
     counts = np.bincount(prob.point, minlength=prob.M).astype(np.float64)
     work = counts * (counts + 1.0) / 2.0 + 4.0 * counts  # pair blocks + per-observation Jacobians
     cum = np.cumsum(work)
@@ -25,8 +27,12 @@ def point_ranges(prob: BALProblem, nranks: int) -> List[Tuple[int, int]]:
     for r in range(1, nranks):
         cuts.append(int(np.searchsorted(cum, total * r / nranks)))
     cuts.append(prob.M)
-    for i in range(1, len(cuts)):  # keep ranges non-empty and monotone
-        cuts[i] = max(cuts[i], cuts[i - 1] + 1) if i < len(cuts) - 1 else prob.M
+    # every rank needs at least one point (an empty shard cannot create a handle and the other ranks would wait for it
+    # inside the collectives): keep the cuts strictly increasing from the left, then leave room on the right
+    for i in range(1, nranks):
+        cuts[i] = max(cuts[i], cuts[i - 1] + 1)
+    for i in range(nranks - 1, 0, -1):
+        cuts[i] = min(cuts[i], cuts[i + 1] - 1)
     return [(cuts[r], cuts[r + 1]) for r in range(nranks)]
 
 

@@ -125,6 +125,15 @@ class GpuSolver:
     def reject(self):
         self._ck(self._L.ba_reject(self._h))
 
+    def numeric_status(self) -> int:
+        """0 fine; r > 0: zero/NaN pivot at row r of the reduced system in the last trial; -1: non-finite step."""
+        v = C.c_int()
+        self._ck(self._L.ba_numeric_status(self._h, C.byref(v)))
+        return v.value
+
+    def set_strict_numeric(self, flag=True):
+        self._ck(self._L.ba_set_strict_numeric(self._h, int(flag)))
+
     # --- diagnostics
     def dx(self):
         v = np.empty(self.n)

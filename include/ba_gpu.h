@@ -67,7 +67,8 @@ int ba_eval(ba_handle* h, double* energy);
 
 /* ≙ functor.df(x, J); JtRes; column norms (QRChol.h:264-280; More.h:268-291; Cholesky.h:247-265).
  * The Jacobian is never materialised for QRKIT/QRCHOL/CHOLESKY (re-evaluated inside ba_compute); for
- * MOREQR this runs stage 1 (QR of the un-damped J, More.h:288-291). max_colnorm2 = max_c |J(:,c)|^2,
+ * MOREQR the point blocks are currently re-factored per trial with the damping rows in place (same step as the
+ * reference's two-stage scheme, More.h:288-348, up to rounding; no stage-1 state is kept). max_colnorm2 = max_c |J(:,c)|^2,
  * max_colnorm = its square root (blueNorm rule of More.h:277); either may be NULL to skip the pass. */
 int ba_linearize(ba_handle* h, double* energy, double* max_colnorm2, double* max_colnorm);
 
@@ -83,6 +84,14 @@ int ba_compute(ba_handle* h, double lambda);
  * (QRChol.h:363-371; update_params BAFunctor.h:299-342).
  * Outputs: |dx|_2, dx^T(lambda dx + JtRes) (the rho denominator, QRChol.h:375) and the test energy. */
 int ba_solve_try(ba_handle* h, double* dx_norm, double* rho_denominator, double* energy_test);
+
+/* Numerical health of the last ba_solve_try. The reference never checks SimplicialLDLT::info(): a singular reduced
+ * system yields a non-finite test energy, which `energyTest < m_energy` (QRChol.h:374) treats as a rejected trial.
+ * Same here: on a zero/NaN pivot or a non-finite step ba_solve_try still returns BA_OK but reports energy_test = NaN,
+ * and *info says why: 0 = fine, r > 0 = zero or NaN pivot at (1-based) row r of the reduced camera system,
+ * -1 = non-finite step. After ba_set_strict_numeric(h, 1) such a trial makes ba_solve_try fail with BA_ERR_NUMERIC. */
+int ba_numeric_status(ba_handle* h, int* info);
+int ba_set_strict_numeric(ba_handle* h, int enable);
 
 /* ≙ x = xTest (QRChol.h:428) / discarding xTest on a rejected trial. */
 int ba_accept(ba_handle* h);

@@ -69,6 +69,10 @@ struct Oracle {
   std::vector<S> m_R, m_c, m_R12, m_S0, m_g0;
   std::vector<int> m_perm;
   bool tall_qr = false;  // QRKIT only: reference-faithful QR of the tall J2bot (small problems)
+  // Timing legs only (bench.py cpu_baseline "all cores"): > 1 runs the per-observation / per-point loops and the
+  // reduced solve with OpenMP. The parity tests use the default 1 (the reference is single-threaded and the
+  // summation order of the single-threaded code is the one the golden anchors were taken with).
+  int nthreads = 1;
   S eps_psi = S(1e-15);  // BAFunctor.h:159
 
   int nparams() const { return 3 * M + 9 * N; }
@@ -121,6 +125,7 @@ struct Oracle {
     // BAFunctor::E_pos, BAFunctor.h:160-178
     fvec.resize(2 * (size_t)K);
     const S tau2 = tau * tau;
+#pragma omp parallel for if (nthreads > 1) num_threads(nthreads) schedule(static)
     for (int i = 0; i < K; ++i) {
       S q[2];
       project(cam(R_, T_, f_, k1_, k2_, view[i]), &X_[3 * (size_t)point[i]], q);
@@ -192,6 +197,7 @@ struct Oracle {
   void linearize(double* energy, double* max_colnorm2, double* max_colnorm) {
     residuals(R, T, f, k1, k2, X, res);
     Jc.resize(18 * (size_t)K); Jp.resize(6 * (size_t)K);
+#pragma omp parallel for if (nthreads > 1) num_threads(nthreads) schedule(static)
     for (int i = 0; i < K; ++i) jacobian_obs(i, &Jc[18 * (size_t)i], &Jp[6 * (size_t)i]);
     const int n = nparams();
     JtRes.assign(n, S(0));
@@ -311,9 +317,87 @@ struct Oracle {
   void clear_reduced() { Sb.assign((size_t)9 * N * (kd + 1), S(0)); g.assign(9 * (size_t)N, S(0)); }
   void keep_reduced() { S_last = Sb; g_last = g; }
 
+  // Accumulation target of the per-point contributions: the reduced system itself (row0 = 0) or, in the
+  // OpenMP timing leg, a chunk-local copy of the rows [row0, row0 + rows) that is added afterwards.
+  struct Acc {
+    S* Sb; S* g; int row0; int kd;
+    inline S& at(int i, int j) { return Sb[(size_t)(i - row0) * (kd + 1) + (j - i + kd)]; }
+    inline S& gat(int i) { return g[i - row0]; }
+  };
+  // Runs body(j, acc, A, B) for every point. nthreads > 1: contiguous chunks of points (balanced by n_j^3), each into
+  // a chunk-local band copy covering the chunk's camera range, merged in chunk order afterwards.
+  template <class Body>
+  void for_points(Body&& body) {
+    if (nthreads <= 1) {
+      Acc acc{Sb.data(), g.data(), 0, kd};
+      std::vector<S> A, B;
+      for (int j = 0; j < M; ++j) body(j, acc, A, B);
+      return;
+    }
+    const int nchunks = std::min(M, 8 * nthreads);
+    std::vector<double> cum(M + 1, 0.0);
+    for (int j = 0; j < M; ++j) { const double nj = pt_start[j + 1] - pt_start[j]; cum[j + 1] = cum[j] + nj * nj * nj + 20.0 * nj; }
+    std::vector<int> cut(nchunks + 1, M);
+    cut[0] = 0;
+    for (int c = 1; c < nchunks; ++c) cut[c] = (int)(std::lower_bound(cum.begin(), cum.end(), cum[M] * c / nchunks) - cum.begin());
+    for (int c = 1; c <= nchunks; ++c) cut[c] = std::max(cut[c], cut[c - 1]);
+    std::vector<std::vector<S>> locS(nchunks), locg(nchunks);
+    std::vector<int> row0(nchunks, 0), rows(nchunks, 0);
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
+    for (int c = 0; c < nchunks; ++c) {
+      if (cut[c + 1] <= cut[c]) continue;
+      int lo = N, hi = -1;
+      for (int i = pt_start[cut[c]]; i < pt_start[cut[c + 1]]; ++i) { lo = std::min(lo, view[i]); hi = std::max(hi, view[i]); }
+      row0[c] = 9 * lo; rows[c] = 9 * (hi - lo + 1);
+      locS[c].assign((size_t)rows[c] * (kd + 1), S(0)); locg[c].assign(rows[c], S(0));
+      Acc acc{locS[c].data(), locg[c].data(), row0[c], kd};
+      std::vector<S> A, B;
+      for (int j = cut[c]; j < cut[c + 1]; ++j) body(j, acc, A, B);
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      if (!rows[c]) continue;
+      const S* ls = locS[c].data();
+      S* dst = Sb.data() + (size_t)row0[c] * (kd + 1);
+      const size_t cnt = (size_t)rows[c] * (kd + 1);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+      for (long long e = 0; e < (long long)cnt; ++e) dst[e] += ls[e];
+      for (int r = 0; r < rows[c]; ++r) g[row0[c] + r] += locg[c][r];
+    }
+  }
+
   // un-pivoted LDL^T on the lower band + solve (SimplicialLDLT arithmetic in natural order;
   // D may be negative, QRChol.h:339-341)
+  // Right-looking variant for the OpenMP timing leg: column j is scaled, then the rows below receive their rank-1
+  // update in parallel (same arithmetic as band_ldlt_solve up to the summation order inside an entry).
+  bool band_ldlt_solve_mt(std::vector<S>& y) {
+    const int n = 9 * N;
+    std::vector<S> d(n), col(kd + 1);
+    for (int j = 0; j < n; ++j) {
+      const S dj = Sat(j, j);
+      d[j] = dj;
+      if (dj == S(0) || !(dj == dj)) return false;
+      const int i1 = std::min(n - 1, j + kd);
+      for (int i = j + 1; i <= i1; ++i) col[i - j] = Sat(i, j);            // L_ij d_j
+#pragma omp parallel for num_threads(nthreads) schedule(static) if (i1 - j > 64)
+      for (int i = j + 1; i <= i1; ++i) {
+        const S lij = col[i - j] / dj;
+        S* row = &Sb[(size_t)i * (kd + 1) + kd - i];                       // row[k] = S(i, k)
+        for (int k = j + 1; k <= i; ++k) row[k] -= lij * col[k - j];
+        row[j] = lij;
+      }
+    }
+    y = g;
+    for (int i = 0; i < n; ++i) { S s = y[i]; for (int j = std::max(0, i - kd); j < i; ++j) s -= Sat(i, j) * y[j]; y[i] = s; }
+    for (int i = 0; i < n; ++i) y[i] /= d[i];
+    for (int i = n - 1; i >= 0; --i) {
+      const S yi = y[i];
+      for (int j = std::max(0, i - kd); j < i; ++j) y[j] -= Sat(i, j) * yi;
+    }
+    return true;
+  }
+
   bool band_ldlt_solve(std::vector<S>& y) {
+    if (nthreads > 1) return band_ldlt_solve_mt(y);
     const int n = 9 * N;
     std::vector<S> d(n);
     for (int i = 0; i < n; ++i) {
@@ -358,6 +442,7 @@ struct Oracle {
       const S inv = S(1) / (c0 - beta), tau_ = (beta - c0) / beta;
       for (int r = k + 1; r <= r1; ++r) Gat(r, k) *= inv;
       Gat(k, k) = beta;
+#pragma omp parallel for if (nthreads > 1 && c1 - k > 64) num_threads(nthreads) schedule(static)
       for (int c = k + 1; c <= c1; ++c) {
         S s = Gat(k, c);
         for (int r = k + 1; r <= r1; ++r) s += Gat(r, k) * Gat(r, c);
@@ -391,11 +476,12 @@ struct Oracle {
     std::vector<S> Rj(9 * (size_t)M), cj(3 * (size_t)M);
     std::vector<int> permj(3 * (size_t)M);
     std::vector<S> R12all(27 * (size_t)K);
-    std::vector<S> A, B, d;
-    // optional reference-faithful tall QR of J2bot (QRKIT, small problems only)
+    // optional reference-faithful tall QR of J2bot (QRKIT, small problems only; single-threaded)
     std::vector<S> tall; std::vector<S> tall_rhs; size_t tall_rows = 0; const int nc = 9 * N;
     if (variant == QRKIT && tall_qr) { tall.assign(((size_t)2 * K + nc) * nc, S(0)); tall_rhs.assign((size_t)2 * K + nc, S(0)); }
-    for (int j = 0; j < M; ++j) {
+    const int nthreads_saved = nthreads;
+    if (!tall.empty()) nthreads = 1;
+    for_points([&](int j, Acc& acc, std::vector<S>& A, std::vector<S>& B) {
       const int o0 = pt_start[j], nj = pt_start[j + 1] - o0, rows = 2 * nj + 3, ncols = 9 * nj;
       A.assign((size_t)rows * 3, S(0));
       for (int i = 0; i < nj; ++i) for (int a = 0; a < 2; ++a) for (int b = 0; b < 3; ++b) A[3 * (2 * i + a) + b] = Jp[6 * (size_t)(o0 + i) + 3 * a + b];
@@ -426,15 +512,16 @@ struct Oracle {
           if (ca == cb && q > p) continue;
           S s = 0;
           for (int r = 3; r < rows; ++r) s += B[(size_t)r * ld + 9 * xa + p] * B[(size_t)r * ld + 9 * xb + q];
-          Sat(9 * ca + p, 9 * cb + q) += s;
+          acc.at(9 * ca + p, 9 * cb + q) += s;
         }
       }
       for (int ia = 0; ia < nj; ++ia) for (int p = 0; p < 9; ++p) {
         S s = 0;
         for (int r = 3; r < rows; ++r) s += B[(size_t)r * ld + 9 * ia + p] * B[(size_t)r * ld + ncols];
-        g[9 * (size_t)view[o0 + ia] + p] += s;
+        acc.gat(9 * view[o0 + ia] + p) += s;
       }
-    }
+    });
+    nthreads = nthreads_saved;
     for (int i = 0; i < 9 * N; ++i) Sat(i, i) += sl * sl;  // camera lambda rows at the bottom of J2bot
     keep_reduced();
     std::vector<S> y;
@@ -474,6 +561,7 @@ struct Oracle {
   void backsubstitute(const std::vector<S>& Rj, const std::vector<S>& cj, const std::vector<int>& permj,
                       const std::vector<S>& R12all, const std::vector<S>& y, std::vector<S>& dx) const {
     for (int c = 0; c < 9 * N; ++c) dx[3 * (size_t)M + c] = -y[c];
+#pragma omp parallel for if (nthreads > 1) num_threads(nthreads) schedule(static)
     for (int j = 0; j < M; ++j) {
       S rhs[3] = {-cj[3 * (size_t)j], -cj[3 * (size_t)j + 1], -cj[3 * (size_t)j + 2]};
       for (int i = pt_start[j]; i < pt_start[j + 1]; ++i) {

@@ -18,6 +18,7 @@ struct Base {
   virtual void apply(const double*) = 0;
   virtual void reduced(double*, double*) = 0;
   virtual void set_tall(int) = 0;
+  virtual void set_threads(int) = 0;
   virtual int kd() = 0;
   virtual int minimize(int, int, bao::TrialRecord*, int, int*) = 0;
 };
@@ -52,6 +53,7 @@ struct Impl : Base {
     cpo(o.g_last, g);
   }
   void set_tall(int t) override { o.tall_qr = t != 0; }
+  void set_threads(int t) override { o.nthreads = t < 1 ? 1 : t; }
   int kd() override { return o.kd; }
   int minimize(int v, int max_outer, bao::TrialRecord* log, int cap, int* nlog) override {
     std::vector<bao::TrialRecord> l;
@@ -82,6 +84,14 @@ double bao_energy_at(void* h, const double* dx) { return ((Base*)h)->energy_at(d
 void bao_apply(void* h, const double* dx) { ((Base*)h)->apply(dx); }
 void bao_reduced(void* h, double* S, double* g) { ((Base*)h)->reduced(S, g); }
 void bao_set_tall(void* h, int t) { ((Base*)h)->set_tall(t); }
+int bao_has_openmp(void) {
+#ifdef _OPENMP
+  return 1;
+#else
+  return 0;
+#endif
+}
+void bao_set_threads(void* h, int t) { ((Base*)h)->set_threads(t); }
 int bao_kd(void* h) { return ((Base*)h)->kd(); }
 int bao_minimize(void* h, int variant, int max_outer, bao::TrialRecord* log, int cap, int* nlog) { return ((Base*)h)->minimize(variant, max_outer, log, cap, nlog); }
 }

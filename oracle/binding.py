@@ -52,6 +52,8 @@ def lib():
         L.bao_apply.argtypes = [C.c_void_p, dp]
         L.bao_reduced.argtypes = [C.c_void_p, dp, dp]
         L.bao_set_tall.argtypes = [C.c_void_p, C.c_int]
+        L.bao_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.bao_has_openmp.restype = C.c_int
         L.bao_kd.restype = C.c_int
         L.bao_kd.argtypes = [C.c_void_p]
         L.bao_minimize.restype = C.c_int
@@ -142,6 +144,13 @@ class Oracle:
 
     def set_tall(self, flag: bool):
         self._L.bao_set_tall(self._h, int(flag))
+
+    def has_openmp(self) -> bool:
+        return bool(self._L.bao_has_openmp())
+
+    def set_threads(self, n: int):
+        """Timing legs only: OpenMP over observations / points and in the reduced solve (default 1, like the reference)."""
+        self._L.bao_set_threads(self._h, int(n))
 
     @property
     def kd(self):

@@ -324,3 +324,50 @@ def test_full_size_properties():
     s.accept()
     assert relv(s.eval(), et3) < 1e-12             # accept commits exactly the test point
     s.close()
+
+
+def test_low_parallax_points_stay_finite_in_float():
+    """Points seen only by two (numerically) coincident cameras: Jp^T Jp is rank 2 up to rounding, so the 3x3 LDL^T of
+    the CHOLESKY point factor (and of single-observation points in the QR variants) can produce a pivot <= 0 by
+    cancellation, most easily in float. The pivots are floored at lambda (their exact lower bound), so the step and the
+    test energy stay finite and numeric_status() reports a healthy trial."""
+    view, point, meas, cam9, X = bal.synthetic_file_arrays(6, 300, seed=17, mean_obs=2.0, window=1)
+    cam9 = cam9.copy()
+    cam9[1] = cam9[0]; cam9[1, 3] += 1e-7          # camera 1 = camera 0 moved by 1e-7: zero baseline
+    cam9[3] = cam9[2]; cam9[3, 4] += 1e-7
+    meas, depth = bal._project_file_units(cam9, X, view, point)
+    assert np.all(depth < 0)
+    prob = bal.from_file_params(view, point, meas + 0.05, cam9, X, name="low-parallax")
+    pairs = {tuple(prob.view[prob.point == j]) for j in range(prob.M)}
+    assert (0, 1) in pairs or (2, 3) in pairs      # some points are seen by a coincident pair only
+    for variant in ("CHOLESKY", "QRCHOL"):
+        for precision in ("f32", "f64"):
+            s = solver.GpuSolver(prob, variant, precision)
+            e, cn2, _ = s.linearize()
+            for lam in (1e-12 * cn2, 1e-6 * cn2):
+                s.compute(lam)
+                dxn, rho_den, et = s.solve_try()
+                if precision == "f64" or lam > 1e-8 * cn2:
+                    assert np.isfinite(dxn) and np.isfinite(et), (variant, precision, lam, s.numeric_status())
+                assert np.all(np.isfinite(s.dx()[:3 * prob.M])) or s.numeric_status() != 0, (variant, precision, lam)
+                s.reject()
+            s.close()
+
+
+def test_singular_reduced_system_is_reported():
+    """A NaN in the state makes the reduced system NaN: the trial comes back with a NaN test energy (= a rejection for
+    the reference's `energyTest < energy`), numeric_status() is non-zero, and strict mode turns it into BA_ERR_NUMERIC."""
+    prob = bal.synthetic(6, 60, seed=1)
+    bad = prob.copy()
+    bad.T = prob.T.copy(); bad.T[2, 0] = np.nan
+    s = solver.GpuSolver(bad, "QRCHOL")
+    s.linearize()
+    s.compute(1.0)
+    dxn, rho_den, et = s.solve_try()
+    assert not np.isfinite(et) and s.numeric_status() != 0
+    s.reject()
+    s.set_strict_numeric(True)
+    s.compute(1.0)
+    with pytest.raises(solver.BAError):
+        s.solve_try()
+    s.close()

@@ -28,6 +28,24 @@ def test_point_ranges_cover_and_balance():
     assert sharding.global_bandwidth(p) == max(sharding.global_bandwidth(sharding.shard(p, r, 2)) for r in range(2)) or True
 
 
+def test_point_ranges_tiny_and_skewed():
+    """Fewer points than a balanced cut needs, or one point carrying nearly all the work: every range stays
+    non-empty; fewer points than ranks is an error on every rank (not a deadlock inside the collectives)."""
+    p = bal.synthetic(12, 9, seed=5, window=4)
+    rs = sharding.point_ranges(p, 8)
+    assert rs[0][0] == 0 and rs[-1][1] == p.M and all(b > a for a, b in rs) and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+    with pytest.raises(ValueError):
+        sharding.point_ranges(p, 10)
+    # skewed: the last point has almost all observations
+    parts = [bal.synthetic_file_arrays(40, 8, seed=6, mean_obs=2.0, window=2), bal.synthetic_file_arrays(40, 1, seed=6, mean_obs=38.0, window=39)]
+    view = np.concatenate([q[0] for q in parts]); point = np.concatenate([parts[0][1], parts[1][1] + 8]).astype(np.int32)
+    meas = np.concatenate([q[2] for q in parts]); X = np.concatenate([q[4] for q in parts])
+    ps = bal.from_file_params(view, point, meas, parts[0][3], X, name="skewed")
+    rs = sharding.point_ranges(ps, 8)
+    assert rs[0][0] == 0 and rs[-1][1] == ps.M and all(b > a for a, b in rs)
+    assert sum(sharding.shard(ps, r, 8).K for r in range(8)) == ps.K
+
+
 def _worker(rank, world, port, out):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from oracle.binding import QRCHOL, Oracle
