@@ -19,6 +19,7 @@
 
 #include "../../include/ba_gpu.h"
 #include "ba_dense.cuh"
+#include "ba_ldlt2.cuh"
 #include "ba_qr.cuh"
 #include "ba_tile.cuh"
 
@@ -284,6 +285,7 @@ struct Impl : ba_handle {
   int cluster_size = 16;  // non-portable size; falls back to 8 when 16 CTAs of this footprint cannot be co-scheduled
   bool solved_in_factor = false;
   int ldlt_roww = 6;  // row-tile warps per chain CTA of the cluster LDLT (BA_LDLT_ROWW=3|6)
+  bool ldlt_v2 = true; // forward elimination of the two-sided scheme by the owner-computes kernel (BA_LDLT_V2=0: first generation)
   DevBuf<double> d_partials, d_scal;
   DevBuf<long long> d_dbg;
   double* h_scal = nullptr;  // pinned
@@ -490,6 +492,9 @@ struct Impl : ba_handle {
     if (std::getenv("BA_FORCE_GRID_LDLT")) force_grid_ldlt = true;
     if (const char* rw = std::getenv("BA_LDLT_ROWW")) ldlt_roww = atoi(rw) == 3 ? 3 : 6;
     if (const char* ts = std::getenv("BA_LDLT_TWOSIDED")) two_sided = atoi(ts) != 0;
+    if (const char* v2 = std::getenv("BA_LDLT_V2")) ldlt_v2 = atoi(v2) != 0;
+    CK(cudaFuncSetAttribute(k_band_ldlt_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ldlt2Smem)));
+    CK(cudaFuncSetAttribute(k_band_ldlt_fwd2, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterSmem<T>)));
     CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     CK(cudaFuncSetAttribute(k_band_qr_backsolve_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -683,6 +688,9 @@ struct Impl : ba_handle {
     return BA_OK;
   }
 
+  static cudaError_t launch_fwd2_impl(const cudaLaunchConfig_t& cfg, const LdltJob<double>& job, long long* dbg) { return cudaLaunchKernelEx(&cfg, k_band_ldlt_fwd2, job, dbg); }
+  static cudaError_t launch_fwd2_impl(const cudaLaunchConfig_t&, const LdltJob<float>&, long long*) { return cudaErrorNotSupported; }
+
   // factorisation of the reduced camera block in d_red (LDL^T or Householder QR of S)
   int factor_reduced() {
     if (variant == BA_QRCHOL || variant == BA_CHOLESKY) {
@@ -700,7 +708,21 @@ struct Impl : ba_handle {
           attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
           cfg.attrs = attr; cfg.numAttrs = 1;
           launches++;
+#ifdef BA_L2_TICKS
+          return cudaLaunchKernelEx(&cfg, k_band_ldlt_cluster<T>, job, (long long*)nullptr, ldlt_roww);  // keep fwd2's counters
+#else
           return cudaLaunchKernelEx(&cfg, k_band_ldlt_cluster<T>, job, d_dbg.p, ldlt_roww);
+#endif
+        };
+        auto launch_fwd2 = [&](const LdltJob<T>& job) -> cudaError_t {  // owner-computes forward elimination (ba_ldlt2.cuh)
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(16 * 2); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = sizeof(Ldlt2Smem); cfg.stream = stream;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr; cfg.numAttrs = 1;
+          launches++;
+          return launch_fwd2_impl(cfg, job, d_dbg.p);
         };
         if (d_W.n < (size_t)nt * NB * NB) CK(d_W.alloc((size_t)nt * NB * NB));
         const int q = (n - (bt + 2) * NB) / (2 * NB);  // panels eliminated from either end by the two-sided scheme
@@ -731,7 +753,8 @@ struct Impl : ba_handle {
           job.sign = T(-1);
           job.p[0] = LdltProblem<T>{A, d_dvec.p, d_W.p, gvec(), d_dx_cam.p, d_info.p, q, 0, 1, 0};
           job.p[1] = LdltProblem<T>{Ar, d_dvec2.p, d_W2.p, gr, d_y2.p, d_info.p, q, 0, 1, 0};
-          CK(launch(job, 2));
+          if (ldlt_v2 && sizeof(T) == 8 && cluster_size == 16 && bt <= L2_MAX_BT) CK(launch_fwd2(job));
+          else CK(launch(job, 2));
           k_band_combine<T><<<64, 256, 0, stream>>>(A, gvec(), Rv, gr, r0, nm);
           LdltJob<T> mid = {};
           mid.sign = T(-1);
