@@ -15,7 +15,9 @@
 //   * the pivot chain is one warp: the owner of the diagonal tile gives it panel k's update first (one DMMA product of
 //     the lower blocks), factors it in registers (warp_ldlt32) while every other warp of the cluster applies panel
 //     k to the rest of the window, and a second warp forms W_{k+1} four columns behind.
-// Per panel: F(k) || U(k-1) | cluster barrier | T(k) | cluster barrier | U(k) || F(k+1) ...; two barriers, no C traffic.
+// One panel of look-ahead, ONE cluster barrier per panel: in iteration k the window receives panel k's update (column
+// k+1 first) while the chain warp factors panel k+1; the four CTAs that own column k+1 then wait for the chain's flag
+// (release/acquire through distributed shared memory) and solve their row tiles; cluster barrier.
 // Only the forward part lives here; the middle block and the backward pass use k_band_ldlt_cluster. double only.
 #pragma once
 #include "ba_dense.cuh"
@@ -40,11 +42,15 @@ struct Ldlt2Smem {
   int sbase[8];                                  // first slot of diagonal class dq (d = d0 + 4 dq)
   int snb[8];                                    // slots of that class
   long long tc[16];                              // phase cycle counters (-DBA_L2_TICKS)
+  int chain_done;                                // this CTA's chain warp published panel p: p + 1 (warp 0 -> warp 4)
+  int panel_ready;                               // W_p, D_p, z_p of panel p are in global memory: p + 1 (written by the diagonal owner's warp 4 into the four CTAs that own column p)
 };
 
 // element (r, c) of a swizzled 32 x 32 tile: 16-byte chunk c/2 of row r sits at chunk (c/2) ^ (2 (r & 3))
 __device__ __forceinline__ int l2_swz(int r, int c) { return r * NB + ((((c >> 1) ^ ((r & 3) << 1)) << 1) | (c & 1)); }
-__device__ __forceinline__ void l2_bar_update() { asm volatile("bar.sync 1, %0;" ::"n"(L2_UT) : "memory"); }
+__device__ __forceinline__ void l2_st_release_cluster(int* p, int v) { asm volatile("st.release.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int l2_ld_acquire_cluster(const int* p) { int v; asm volatile("ld.acquire.cluster.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void l2_bar_update(const int nthr) { asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); }
 
 // acc (accumulator order, e = 2 (4 mi + ni) + h <-> row 8 mi + lane/4, column 8 ni + 2 (lane%4) + h) += A (ms B)^T.
 // MODE 0: all 16 blocks; 1: lower blocks only (ni <= mi: symmetric diagonal tile); 2: B lower triangular (W_k): k-steps
@@ -133,12 +139,13 @@ __device__ __forceinline__ void l2_acc_to_smem(double* s, const int lane, const 
       *reinterpret_cast<double2*>(s + l2_swz(mi * 8 + lr, ni * 8 + 2 * lc)) = make_double2(acc[2 * (4 * mi + ni)], acc[2 * (4 * mi + ni) + 1]);
 }
 // tile (t, column offset c0) of the band matrix -> swizzled shared-memory tile, by `nthr` threads (this one is `tix`).
-// Interior tiles travel as 16-byte cp.async (caller commits / waits), edge tiles as masked loads + shared stores.
+// Tiles whose rows all exist travel as 16-byte cp.async (caller commits / waits), INCLUDING the positions outside the
+// band (they alias other rows of the band storage): l2_fix_tile zeroes those afterwards, each thread the chunks it
+// copied itself, so no barrier is needed in between. Tiles reaching past row n take masked loads + shared stores.
 __device__ __forceinline__ void l2_stage_tile(double* dst, const BandMat<double>& A, const int t, const int c0, const int tix, const int nthr) {
   const int row0 = t * NB, lds = (int)A.lds;
   const double* tp = A.v + (size_t)row0 * lds + c0;
-  const bool interior = (row0 + NB - 1 < A.n) && (row0 + NB - 1 - c0 <= A.kd) && (row0 >= c0 + NB);
-  if (interior) {
+  if (row0 + NB - 1 < A.n && row0 >= c0 + NB) {
     for (int q = tix; q < NB * NB / 2; q += nthr) {
       const int r = q >> 4, ch = q & 15;
       cp_async16(dst + r * NB + ((ch ^ ((r & 3) << 1)) << 1), tp + r * lds + 2 * ch);
@@ -152,6 +159,17 @@ __device__ __forceinline__ void l2_stage_tile(double* dst, const BandMat<double>
     }
   }
 }
+__device__ __forceinline__ void l2_fix_tile(double* dst, const BandMat<double>& A, const int t, const int c0, const int tix, const int nthr) {
+  const int row0 = t * NB;
+  if (row0 + NB - 1 < A.n && row0 >= c0 + NB && row0 + NB - 1 - c0 > A.kd) {
+    for (int q = tix; q < NB * NB / 2; q += nthr) {
+      const int r = q >> 4, ch = q & 15, dlt = row0 + r - (c0 + 2 * ch);
+      double* e = dst + r * NB + ((ch ^ ((r & 3) << 1)) << 1);
+      if (dlt > A.kd) e[0] = 0.0;
+      if (dlt - 1 > A.kd) e[1] = 0.0;
+    }
+  }
+}
 // swizzled shared-memory tile -> tile (t, c0) of the band matrix with coalesced 16-byte stores (one warp)
 __device__ __forceinline__ void l2_smem_to_tile(const double* s, const BandMat<double>& A, const int t, const int c0, const int lane) {
   const int row0 = t * NB, lds = (int)A.lds;
@@ -160,6 +178,72 @@ __device__ __forceinline__ void l2_smem_to_tile(const double* s, const BandMat<d
 #pragma unroll 4
   for (int q = lane; q < NB * NB / 2; q += 32) {
     const int r = q >> 4, ch = q & 15;
+    const double2 v = *reinterpret_cast<const double2*>(s + r * NB + ((ch ^ ((r & 3) << 1)) << 1));
+    if (interior) {
+      *reinterpret_cast<double2*>(tp + r * lds + 2 * ch) = v;
+    } else {
+      const int gi = row0 + r, gj = c0 + 2 * ch;
+      if (gi < A.n && gj <= gi && gi - gj <= A.kd) tp[r * lds + 2 * ch] = v.x;
+      if (gi < A.n && gj + 1 <= gi && gi - gj - 1 <= A.kd) tp[r * lds + 2 * ch + 1] = v.y;
+    }
+  }
+}
+
+// ---- half tiles (rows 16 h .. 16 h + 15: accumulator blocks mi = 2 h, 2 h + 1) for the T phase, where the <= 5 row
+// tiles of a CTA are spread over all eight warps
+__device__ __forceinline__ void l2_load_slot_half(const double* s, const int lane, const int h, double (&acc)[16]) {
+#pragma unroll
+  for (int p = 0; p < 8; ++p) { const double2 v = *reinterpret_cast<const double2*>(s + (8 * h + p) * 64 + 2 * lane); acc[2 * p] = v.x; acc[2 * p + 1] = v.y; }
+}
+__device__ __forceinline__ void l2_load_tile_half(const BandMat<double>& A, const int ti, const int tj, const int lane, const int h, double (&acc)[16]) {
+  const int lr = lane >> 2, lc = lane & 3, row0 = ti * NB, col0 = tj * NB, lds = (int)A.lds;
+  const double* tp = A.v + (size_t)row0 * lds + col0;
+  const double* zp = ba_zero_word;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int r = (2 * h + (e >> 3)) * 8 + lr, c = ((e >> 1) & 3) * 8 + 2 * lc + (e & 1), gi = row0 + r, gj = col0 + c;
+    const bool ok = gi < A.n && gj <= gi && gi - gj <= A.kd;
+    acc[e] = *(ok ? tp + r * lds + c : zp);
+  }
+}
+__device__ __forceinline__ void l2_acc_to_smem_half(double* s, const int lane, const int h, const double (&acc)[16]) {
+  const int lr = lane >> 2, lc = lane & 3;
+#pragma unroll
+  for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+      *reinterpret_cast<double2*>(s + l2_swz((2 * h + ml) * 8 + lr, ni * 8 + 2 * lc)) = make_double2(acc[2 * (4 * ml + ni)], acc[2 * (4 * ml + ni) + 1]);
+}
+// acc (two row blocks) += A_half W^T, W lower triangular
+__device__ __forceinline__ void l2_mma_half_w(const double* __restrict__ sA, const double* __restrict__ sW, const int lane, const int h, double (&acc)[16]) {
+  const int lr = lane >> 2, lc = lane & 3, xr = (lr & 3) << 1;
+  const double* pa = sA + (16 * h + lr) * NB;
+  const double* pb = sW + lr * NB;
+#pragma unroll
+  for (int kk = 0; kk < NB / 4; ++kk) {
+    const int off = ((((kk << 1) | (lc >> 1)) ^ xr) << 1) | (lc & 1);
+    double af[2], bf[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) af[i] = pa[i * 8 * NB + off];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bf[i] = pb[i * 8 * NB + off];
+#pragma unroll
+    for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        if (kk > 2 * ni + 1) continue;
+        dmma884(acc[2 * (4 * ml + ni)], acc[2 * (4 * ml + ni) + 1], af[ml], bf[ni]);
+      }
+  }
+}
+// rows 16 h .. 16 h + 15 of a swizzled shared-memory tile -> tile (t, c0) of the band matrix (one warp, 16-byte stores)
+__device__ __forceinline__ void l2_smem_to_tile_half(const double* s, const BandMat<double>& A, const int t, const int c0, const int lane, const int h) {
+  const int row0 = t * NB, lds = (int)A.lds;
+  double* tp = A.v + (size_t)row0 * lds + c0;
+  const bool interior = (row0 + NB - 1 < A.n) && (row0 + NB - 1 - c0 <= A.kd) && (row0 >= c0 + NB);
+#pragma unroll 4
+  for (int q = lane; q < NB * NB / 4; q += 32) {
+    const int r = 16 * h + (q >> 4), ch = q & 15;
     const double2 v = *reinterpret_cast<const double2*>(s + r * NB + ((ch ^ ((r & 3) << 1)) << 1));
     if (interior) {
       *reinterpret_cast<double2*>(tp + r * lds + 2 * ch) = v;
@@ -222,7 +306,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
   if (tid < 2 * NB) { sm.pn.sCol[0][NB + (tid & 31)] = 0.0; sm.pn.sCol[1][NB + (tid & 31)] = 0.0; }
   if (tid < 16) sm.tc[tid] = 0;
   if (tid == 0) {
-    sm.pn.progress = 0;
+    sm.pn.progress = 0; sm.chain_done = 0; sm.panel_ready = 0;
     const int d0 = (r - c + 4) & 3;
     int b = 0;
     for (int dq = 0; dq < 8; ++dq) {
@@ -255,15 +339,91 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
     }
     dvec[k0 + lane] = d;
     if (k0 + lane < n) { rhs[k0 + lane] = sm.pn.sz[lane] * sm.pn.sinvd[lane]; zscr[k0 + lane] = sm.pn.sz[lane]; }
+    __syncwarp();
+    if (lane == 0) st_release_cta(&sm.chain_done, k + 1);
   };
   auto form_w = [&](const int k) {
     double a[NB];
 #pragma unroll
     for (int cc = 0; cc < NB; ++cc) a[cc] = (cc == lane) ? 1.0 : 0.0;
     l2_warp_w32(a, sm.pn, Wbuf + (size_t)k * NB * NB + lane, 64 * (k + 1));
+    __syncwarp();
+    // W_k is out; once the chain warp has published D_k, z_k and the diagonal tile too, tell the owners of column k
+    if (lane < 4) {
+      while (ld_acquire_cta(&sm.chain_done) < k + 1) {}
+      l2_st_release_cluster(cluster.map_shared_rank(&sm.panel_ready, 4 * lane + (k & 3)), k + 1);
+    }
+    __syncwarp();
   };
 
-  // ---- F(0)
+  // ---- T(k): L(i, k) = T(i, k) W_k^T D_k^-1 on the CTAs that own column k, once the chain has published panel k. All eight
+  // warps; unit q = (tile q / 2, half q % 2), warp w takes the units w and w + 8.
+  auto solve_column = [&](const int k) {
+    const int k0 = k * NB, hi = min(k + bt, nt - 1);
+    const int ia0 = (k + 1) + ((r - (k + 1)) & 3);
+    __syncthreads();                                   // this CTA's window updates (and its chain warps) are done
+    if (lane == 0) { while (l2_ld_acquire_cluster(&sm.panel_ready) < k + 1) {} }
+    __syncwarp();
+    (void)l2_ld_acquire_cluster(&sm.panel_ready);
+    {
+      for (int q = tid; q < NB * NB / 2; q += CL_THREADS) {   // W_k -> opB[0]
+        const int rr = q >> 4, ch = q & 15;
+        cp_async16(sm.opB[0] + rr * NB + ((ch ^ ((rr & 3) << 1)) << 1), Wbuf + (size_t)k * NB * NB + rr * NB + 2 * ch);
+      }
+      cp_async_commit();
+      if (tid < NB) { const double d = dvec[k0 + tid]; sm.sinvdT[tid] = pivot_rcp(d); sm.szT[tid] = *((k0 + tid < n) ? zscr + k0 + tid : zp); }
+      const int ntile = (hi >= ia0) ? ((hi - ia0) >> 2) + 1 : 0;
+      const int lr = lane >> 2, lc = lane & 3;
+      double rold[2][2];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int q = warp + 8 * v;
+        rold[v][0] = rold[v][1] = 0.0;
+        if (q < 2 * ntile) {
+          const int t = q >> 1, h = q & 1, i = ia0 + 4 * t;
+          double acc[16];
+          if (k > max(0, i - bt)) l2_load_slot_half(slot_of(i, k), lane, h, acc);   // received at least one update: lives in its slot
+          else l2_load_tile_half(A, i, k, lane, h, acc);
+          l2_acc_to_smem_half(sm.opA[t], lane, h, acc);
+#pragma unroll
+          for (int ml = 0; ml < 2; ++ml) { const int gi = i * NB + (2 * h + ml) * 8 + lr; rold[v][ml] = *((lc == 0 && gi < n) ? rhs + gi : zp); }
+        }
+      }
+      cp_async_wait_all();
+      __syncthreads();
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int q = warp + 8 * v;
+        if (q < 2 * ntile) {
+          const int t = q >> 1, h = q & 1, i = ia0 + 4 * t;
+          double x[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) x[e] = 0.0;
+          l2_mma_half_w(sm.opA[t], sm.opB[0], lane, h, x);
+          double part[2] = {0.0, 0.0};
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int col = ((e >> 1) & 3) * 8 + 2 * lc + (e & 1);
+            x[e] *= sm.sinvdT[col];
+            part[e >> 3] += x[e] * sm.szT[col];
+          }
+#pragma unroll
+          for (int ml = 0; ml < 2; ++ml) {
+            part[ml] += __shfl_xor_sync(FULL, part[ml], 1);
+            part[ml] += __shfl_xor_sync(FULL, part[ml], 2);
+            const int gi = i * NB + (2 * h + ml) * 8 + lr;
+            if (lc == 0 && gi < n) rhs[gi] = rold[v][ml] - part[ml];
+          }
+          __syncwarp();
+          l2_acc_to_smem_half(sm.opA[t], lane, h, x);
+          __syncwarp();
+          l2_smem_to_tile_half(sm.opA[t], A, i, k0, lane, h);
+        }
+      }
+    }
+  };
+
+  // ---- F(0), T(0)
   if (np_fwd > 0 && rank == diag_owner(0)) {
     if (warp == 0) {
       double a[NB];
@@ -280,75 +440,35 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
       form_w(0);
     }
   }
+  if (np_fwd > 0 && c == 0) solve_column(0);
   cluster.sync();
 
   for (int k = 0; k < np_fwd; ++k) {
     const int k0 = k * NB, hi = min(k + bt, nt - 1);
     const int ia0 = (k + 1) + ((r - (k + 1)) & 3);     // first tile row >= k+1 owned by this CTA row
     const int jb0 = (k + 1) + ((c - (k + 1)) & 3);     // first tile column >= k+1 owned by this CTA column
-    // ======================= T(k): L(i, k) = T(i, k) W_k^T D_k^-1 on the CTAs that own column k
-    if (upd_warp && c == (k & 3)) {
-      for (int q = ut; q < NB * NB / 2; q += L2_UT) {   // W_k -> opB[0]
-        const int rr = q >> 4, ch = q & 15;
-        cp_async16(sm.opB[0] + rr * NB + ((ch ^ ((rr & 3) << 1)) << 1), Wbuf + (size_t)k * NB * NB + rr * NB + 2 * ch);
-      }
-      cp_async_commit();
-      if (ut < NB) { const double d = dvec[k0 + ut]; sm.sinvdT[ut] = pivot_rcp(d); sm.szT[ut] = *((k0 + ut < n) ? zscr + k0 + ut : zp); }
-      const int i = ia0 + 4 * u;
-      const bool have = (u < L2_NOP) && (i <= hi);
-      double acc[32];
-      if (have) {
-        const bool resident = k > max(0, i - bt);      // received at least one update: lives in its slot
-        if (resident) l2_load_slot(slot_of(i, k), lane, acc); else l2_load_tile(A, i, k, lane, acc);
-        l2_acc_to_smem(sm.opA[u], lane, acc);
-      }
-      cp_async_wait_all();
-      l2_bar_update();
-      if (have) {
-        double x[32], ms[NB / 4];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) x[e] = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < NB / 4; ++kk) ms[kk] = 1.0;
-        l2_mma<2>(sm.opA[u], sm.opB[0], ms, lane, x);
-        const int lr = lane >> 2, lc = lane & 3;
-        double part[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int col = ((e >> 1) & 3) * 8 + 2 * lc + (e & 1);
-          x[e] *= sm.sinvdT[col];
-          part[e >> 3] += x[e] * sm.szT[col];
-        }
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-          part[mi] += __shfl_xor_sync(FULL, part[mi], 1);
-          part[mi] += __shfl_xor_sync(FULL, part[mi], 2);
-          const int gi = i * NB + mi * 8 + lr;
-          if (lc == 0 && gi < n) rhs[gi] -= part[mi];
-        }
-        __syncwarp();
-        l2_acc_to_smem(sm.opA[u], lane, x);
-        __syncwarp();
-        l2_smem_to_tile(sm.opA[u], A, i, k0, lane);
-      }
-    }
-    if (warp == 1) L2TICK(5)
-    cluster.sync();
-    if (warp == 1) L2TICK(9)
-    if (warp == 0) L2TICK(11)
     // ======================= U(k): the window receives panel k's update; F(k+1) on the owner of the next diagonal tile
     const bool prio = (k + 1 < np_fwd);                 // the tile (k+1, k+1) goes to the chain warp
     const bool last = (k == np_fwd - 1);                // last panel: updated tiles also return to the band storage
-    if (upd_warp) {
+    const bool chain_here = prio && rank == diag_owner(k + 1);   // warps 0 and 4 of this CTA run the chain of panel k+1
+    const int nuw = chain_here ? L2_UW : CL_WARPS;               // otherwise they update like everybody else
+    const int uw = chain_here ? (upd_warp ? u : -1) : warp;
+    if (uw >= 0) {
+      const int nthr = 32 * nuw, utx = 32 * uw + lane;
       for (int t = 0, i = ia0; i <= hi; ++t, i += 4) {
         if (prio && i == k + 1) continue;               // only the diagonal tile uses this row: staged by the chain warp
-        l2_stage_tile(sm.opA[t], A, i, k0, ut, L2_UT);
+        l2_stage_tile(sm.opA[t], A, i, k0, utx, nthr);
       }
-      for (int t = 0, j = jb0; j <= hi; ++t, j += 4) l2_stage_tile(sm.opB[t], A, j, k0, ut, L2_UT);
+      for (int t = 0, j = jb0; j <= hi; ++t, j += 4) l2_stage_tile(sm.opB[t], A, j, k0, utx, nthr);
       cp_async_commit();
-      if (ut < NB) sm.sdU[ut] = dvec[k0 + ut];
+      if (utx < NB) sm.sdU[utx] = dvec[k0 + utx];
       cp_async_wait_all();
-      l2_bar_update();
+      for (int t = 0, i = ia0; i <= hi; ++t, i += 4) {
+        if (prio && i == k + 1) continue;
+        l2_fix_tile(sm.opA[t], A, i, k0, utx, nthr);
+      }
+      for (int t = 0, j = jb0; j <= hi; ++t, j += 4) l2_fix_tile(sm.opB[t], A, j, k0, utx, nthr);
+      l2_bar_update(nthr);
       if (warp == 1) L2TICK(6)
       double ms[NB / 4];
 #pragma unroll
@@ -358,19 +478,20 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
         const int i0 = j + ((r - j) & 3);
         for (int i = i0; i <= hi; i += 4) {
           if (prio && i == k + 1 && j == k + 1) continue;
-          if (t % L2_UW == u) {
+          if (t % nuw == uw) {
             double acc[32];
             double* s = slot_of(i, j);
             const bool first = (k == max(0, i - bt));
             if (first) l2_load_tile(A, i, j, lane, acc); else l2_load_slot(s, lane, acc);
-            l2_mma<0>(sm.opA[(i - ia0) >> 2], sm.opB[jt], ms, lane, acc);
+            if (i == j) l2_mma<1>(sm.opA[(i - ia0) >> 2], sm.opB[jt], ms, lane, acc);
+            else l2_mma<0>(sm.opA[(i - ia0) >> 2], sm.opB[jt], ms, lane, acc);
             if (last) l2_store_tile(A, i, j, lane, acc); else l2_store_slot(s, lane, acc);
           }
           ++t;
         }
       }
       if (warp == 1) L2TICK(7)
-    } else if (prio && rank == diag_owner(k + 1)) {
+    } else {   // chain_here: warps 0 and 4
       const int k1 = k + 1;
       if (warp == 0) {
         l2_stage_tile(sm.opA[0], A, k1, k0, lane, 32);  // L(k+1, k): both operands of the diagonal update
@@ -382,6 +503,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
         const int gi = k1 * NB + lane;
         const double z = *((gi < n) ? rhs + gi : zp);
         cp_async_wait_all();
+        l2_fix_tile(sm.opA[0], A, k1, k0, lane, 32);
         __syncwarp();
         L2TICK(0)
         l2_mma<1>(sm.opA[0], sm.opA[0], ms, lane, acc);
@@ -412,8 +534,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
         form_w(k1);
       }
     }
-    cluster.sync();
     if (warp == 1) L2TICK(8)
+    if (prio && c == ((k + 1) & 3)) solve_column(k + 1);
+    if (warp == 1) L2TICK(5)
+    cluster.sync();
+    if (warp == 1) L2TICK(9)
     if (warp == 0) L2TICK(12)
   }
 #ifdef BA_L2_TICKS
