@@ -276,6 +276,8 @@ struct Impl : ba_handle {
   DevBuf<int> d_seg, d_obs_of_slot, d_unit_pt, d_big_pt, d_huge_pt;  // warp units (points with <= 32 observations) / tiles of the larger points / points with > TILE observations
   int nunits = 0, nbig = 0, nhuge = 0, huge_max = 0;
   DevBuf<T> d_P, d_D, d_Pt;  // per-observation (P, D) / per-point records written by k_point_factor*
+  DevBuf<T> d_J, d_Pt0;      // MOREQR stage 1 (un-damped point QR, once per outer iteration): J records, point records
+  bool two_stage = false, stage1_valid = false;
   int nblocks = 0, gather_grid = 0;
   DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g | gJ */, d_keep, d_dvec, d_tmp;
   DevBuf<T> d_qr;  // general band copy for the Householder QR of S
@@ -381,6 +383,15 @@ struct Impl : ba_handle {
       j = j1;
     }
     nunits = (int)unit_pt.size() / 2; nbig = (int)big_pt.size() / 2;
+    // MOREQR two-stage scheme (More.h:288-348) for the points handled by the warp kernel; a point with a single
+    // observation has a rank-2 un-damped block (2 x 3), which the segmented Householder does not cover: such inputs
+    // (none in the BAL files: every point has >= 2 observations) fall back to re-factoring the damped blocks per trial
+    {
+      bool single = false;
+      for (int j = 0; j < M && !single; ++j) single = (pt_start[j + 1] - pt_start[j]) == 1;
+      const char* ts = std::getenv("BA_MOREQR_TWOSTAGE");
+      two_stage = (variant == BA_MOREQR) && !single && nunits > 0 && !(ts && atoi(ts) == 0);
+    }
     // static structure of the Schur gather: camera-major record slots, non-empty camera-pair blocks, pair lists
     std::vector<int> cam_start(N + 1, 0), slot(K);
     for (int i = 0; i < K; ++i) cam_start[view[i] + 1]++;
@@ -448,6 +459,7 @@ struct Impl : ba_handle {
     CK(d_counter.alloc(1));
     CK(d_pairs.alloc(pairs.size()));
     CK(d_P.alloc((size_t)K * REC)); CK(d_D.alloc((size_t)K * REC)); CK(d_Pt.alloc((size_t)M * PREC));
+    if (two_stage) { CK(d_J.alloc((size_t)K * REC)); CK(d_Pt0.alloc((size_t)M * PREC)); }
     CK(cudaMemcpyAsync(d_slot.p, slot.data(), K * sizeof(int), cudaMemcpyHostToDevice, stream));
     {
       std::vector<int> inv(K);   // observation stored at each camera-major slot (column norms of the camera columns)
@@ -563,7 +575,7 @@ struct Impl : ba_handle {
       CK(cudaMemcpyAsync(d_X.p, x, nx * sizeof(T), cudaMemcpyHostToDevice, stream));
     }
     CK(cudaStreamSynchronize(stream));
-    computed = tried = linearized = false;
+    computed = tried = linearized = false; stage1_valid = false;
     return BA_OK;
   }
 
@@ -612,9 +624,22 @@ struct Impl : ba_handle {
     return BA_OK;
   }
 
+  // MOREQR stage 1: QR of the un-damped point blocks at the current x (More.h:288-291), once per outer iteration
+  int moreqr_stage1() {
+    TileArgs<T> a0 = tile_args(T(0));
+    a0.factor = PF_HOUSEHOLDER;
+    k_point_factor_warp<T, true><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, point_factor_warp_smem_bytes<T>(), stream>>>(a0, nunits, d_unit_pt.p, d_seg.p, d_slot.p,
+                                                                                                                     d_J.p, nullptr, d_Pt0.p);
+    launches++;
+    CK(cudaGetLastError());
+    stage1_valid = true;
+    return BA_OK;
+  }
+
   int linearize(double* energy, double* max_cn2, double* max_cn) override {
     CK(cudaSetDevice(device));
     const int nb = (K + 255) / 256;
+    if (two_stage) { int rc1 = moreqr_stage1(); if (rc1) return rc1; }
     if (max_cn2 || max_cn) {
       const size_t np = 3 * (size_t)M + 9 * (size_t)N;
       if (d_tmp.n < np) CK(d_tmp.alloc(np));
@@ -654,7 +679,13 @@ struct Impl : ba_handle {
     const T diag = (variant == BA_CHOLESKY) ? lamT : sl * sl;  // QR variants square the sqrt(lambda) rows
     mark(0);
     CK(cudaMemsetAsync(d_red.p, 0, (red_count + 2 * (size_t)n) * sizeof(T), stream));
-    if (nunits) { k_point_factor_warp<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, point_factor_warp_smem_bytes<T>(), stream>>>(tile_args(lamT), nunits, d_unit_pt.p, d_seg.p, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++; }
+    if (two_stage) {
+      // per lambda trial only the 6x3 blocks [R0_j; sqrt(lambda) I3] are re-triangularised (More.h:293-348)
+      if (!stage1_valid) { int rc1 = moreqr_stage1(); if (rc1) return rc1; }
+      k_moreqr_stage2<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, point_factor_warp_smem_bytes<T>(), stream>>>(lamT, nunits, d_unit_pt.p, d_seg.p, d_slot.p, d_point.p,
+                                                                                                                 d_J.p, d_Pt0.p, d_P.p, d_D.p, d_Pt.p);
+      launches++;
+    } else if (nunits) { k_point_factor_warp<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, point_factor_warp_smem_bytes<T>(), stream>>>(tile_args(lamT), nunits, d_unit_pt.p, d_seg.p, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++; }
     if (nbig) {
       TileArgs<T> ab = tile_args(lamT); ab.tile_pt = d_big_pt.p;
       k_point_factor<T><<<nbig, TILE, sizeof(TileSmem<T>), stream>>>(ab, 2, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++;
@@ -912,7 +943,7 @@ struct Impl : ba_handle {
     if (!tried) return fail(BA_ERR_STATE, "ba_accept called without a trial step");
     std::swap(d_cams.p, d_cams_test.p);
     std::swap(d_X.p, d_X_test.p);
-    computed = tried = linearized = false;
+    computed = tried = linearized = false; stage1_valid = false;
     return BA_OK;
   }
   int reject() override { tried = false; return BA_OK; }
@@ -1061,7 +1092,7 @@ struct Impl : ba_handle {
 extern "C" {
 
 const char* ba_last_error(void) { return g_err.c_str(); }
-const char* ba_version(void) { return "ba_b200 0.3 (sm_100a; kernels: k_point_factor_warp/_big, k_schur_diag/gather, k_band_ldlt_cluster, k_band_qr_reg/_tall, k_backsub_eval/_big)"; }
+const char* ba_version(void) { return "ba_b200 0.4 (sm_100a; kernels: k_point_factor_warp/_big, k_moreqr_stage2, k_schur_diag/gather, k_band_ldlt_cluster, k_band_ldlt_fwd2, k_band_qr_reg/_tall, k_backsub_eval/_big)"; }
 
 int ba_create(ba_handle** out, int N, int M, int K, const int* view, const int* point, const double* meas,
               double inlier_threshold, int precision, int variant, int device) {

@@ -553,7 +553,11 @@ template <class T> constexpr size_t point_factor_warp_smem_bytes() { return (siz
 #ifndef BA_PF_MIN_BLOCKS
 #define BA_PF_MIN_BLOCKS 4
 #endif
-template <class T>
+// STAGE1 (MOREQR, BacktrackLevMarqMore.h:288-291: QR of the UN-damped J once per outer iteration): the kernel is run
+// with lambda = 0 and stores, instead of the P / D records of a trial, one J record per observation at the observation's
+// index (passed as `Prec`): Jc_i 2x9 | thin Q0 rows of the observation 2x3 | e_i | 2 pad, and the point record
+// (R0, c0 = Q0^T e, G, perm0) into `Ptrec`; k_moreqr_stage2 turns them into the records of a trial.
+template <class T, bool STAGE1 = false>
 __global__ void __launch_bounds__(TILE, BA_PF_MIN_BLOCKS) k_point_factor_warp(TileArgs<T> a, int nunits, const int* __restrict__ unit_obs, const int* __restrict__ seg, const int* __restrict__ slot,
                                                             T* __restrict__ Prec, T* __restrict__ Drec, T* __restrict__ Ptrec) {
   constexpr unsigned FULL = 0xffffffffu;
@@ -608,11 +612,19 @@ __global__ void __launch_bounds__(TILE, BA_PF_MIN_BLOCKS) k_point_factor_warp(Ti
   const int rsub = lane / CPR, part = lane - rsub * CPR;
   const bool cpl = lane < RPI * CPR;
   T rec[REC];
+  if (STAGE1) {
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
+    for (int b = 0; b < 18; ++b) rec[b] = jc[b];
 #pragma unroll
-    for (int b = 0; b < 9; ++b) rec[9 * k + b] = x[0][k] * jc[b] + x[1][k] * jc[9 + b];
-  rec[27] = T(0);
+    for (int k = 0; k < 3; ++k) { rec[18 + k] = x[0][k]; rec[21 + k] = x[1][k]; }
+    rec[24] = e0; rec[25] = e1; rec[26] = T(0); rec[27] = T(0);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int b = 0; b < 9; ++b) rec[9 * k + b] = x[0][k] * jc[b] + x[1][k] * jc[9 + b];
+    rec[27] = T(0);
+  }
   store_rec(my + lane * SR, rec);
   __syncwarp();
 #pragma unroll
@@ -622,17 +634,19 @@ __global__ void __launch_bounds__(TILE, BA_PF_MIN_BLOCKS) k_point_factor_warp(Ti
       *reinterpret_cast<int4*>(Prec + (size_t)(o0 + r) * REC + part * EPC) = *reinterpret_cast<const int4*>(my + r * SR + part * EPC);
   }
   __syncwarp();
+  if (!STAGE1) {
 #pragma unroll
-  for (int b = 0; b < 18; ++b) rec[b] = jc[b];
-  fill_drec_tail<T>(rec, x[0][0], x[0][1], x[0][2], x[1][0], x[1][1], x[1][2], cq[0], cq[1], cq[2], e0, e1);
-  store_rec(my + lane * SR, rec);
-  __syncwarp();
+    for (int b = 0; b < 18; ++b) rec[b] = jc[b];
+    fill_drec_tail<T>(rec, x[0][0], x[0][1], x[0][2], x[1][0], x[1][1], x[1][2], cq[0], cq[1], cq[2], e0, e1);
+    store_rec(my + lane * SR, rec);
+    __syncwarp();
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const int r = RPI * q + rsub;
-    const size_t slr = (size_t)__shfl_sync(FULL, (int)sl, r & 31);
-    if (cpl && r < un)
-      *reinterpret_cast<int4*>(Drec + slr * REC + part * EPC) = *reinterpret_cast<const int4*>(my + r * SR + part * EPC);
+    for (int q = 0; q < NQ; ++q) {
+      const int r = RPI * q + rsub;
+      const size_t slr = (size_t)__shfl_sync(FULL, (int)sl, r & 31);
+      if (cpl && r < un)
+        *reinterpret_cast<int4*>(Drec + slr * REC + part * EPC) = *reinterpret_cast<const int4*>(my + r * SR + part * EPC);
+    }
   }
   if (!act) return;
   if (i == 0) {
@@ -1063,6 +1077,186 @@ __global__ void __launch_bounds__(TILE, 4) k_backsub_eval(TileArgs<T> a, const T
     double s = 0.0;
     for (int w = 0; w < TILE / 32; ++w) s += red[t * (TILE / 32) + w];
     partials[(size_t)t * ntiles + tile] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MOREQR stage 2 (BacktrackLevMarqMore.h:293-348): per lambda trial only the 6x3 block [R0_j; sqrt(lambda) I3] of every
+// point is re-triangularised (column-pivoted Householder, the conventions of the per-point QR above):
+//   [R0; sqrt(lambda) I3] P' = Q' [R'; 0].   With Jp P0 = Q0 R0 from stage 1:  [Jp; sqrt(lambda) I3] P0 P' = Q [R'; 0],
+// the observation rows of the thin Q being Q0_i Q'_11 (Q'_11 = top-left 3x3 of Q'). Hence, per observation,
+//   Q1_i = Q0_i Q'_11,  R12'_i = Q1_i^T Jc_i,  c' = Q'_11^T c0,  M_i = I2 - Q1_i Q1_i^T,  w_i = e_i - Q1_i c',
+// i.e. exactly the P / D / point records k_point_factor_warp writes for a trial, computed from the stage-1 J records
+// without re-evaluating the Jacobian or re-factoring the (2 n_j + 3) x 3 block; the reduced-system kernels and the
+// back-substitution then run unchanged (dx_j = P0 P' z: the two permutations are composed in the point record).
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void moreqr_inner_qr(const T (&R0)[6], const T sl, T (&R)[6], int& pm, T (&Q11)[3][3]) {
+  const T tiny = (sizeof(T) == 8 ? T(2.2250738585072014e-308) : T(1.17549435e-38f));
+  T A[6][3] = {{R0[0], R0[1], R0[2]}, {T(0), R0[3], R0[4]}, {T(0), T(0), R0[5]}, {sl, T(0), T(0)}, {T(0), sl, T(0)}, {T(0), T(0), sl}};
+  T tau[3];
+  int pmv[3] = {0, 1, 2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    T nn[3] = {T(0), T(0), T(0)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c >= k) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) if (r >= k) nn[c] += A[r][c] * A[r][c];
+      }
+    int best = k;
+    T bestv = nn[k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c > k && nn[c] > bestv) { best = c; bestv = nn[c]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c > k) {
+        const bool sw = best == c;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) cswap(A[r][k], A[r][c], sw);
+        const int t = pmv[k]; pmv[k] = sw ? pmv[c] : pmv[k]; pmv[c] = sw ? t : pmv[c];
+      }
+    }
+    const T c0 = A[k][k];
+    T tail2 = T(0);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) if (r > k) tail2 += A[r][k] * A[r][k];
+    const bool degenerate = tail2 <= tiny;
+    T beta = tsqrt(c0 * c0 + tail2);
+    if (c0 >= T(0)) beta = -beta;
+    if (degenerate) beta = c0;
+    const T inv = degenerate ? T(0) : T(1) / (c0 - beta);
+    const T tk = degenerate ? T(0) : (beta - c0) / beta;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) if (r > k) A[r][k] *= inv;
+    A[k][k] = beta;
+    tau[k] = tk;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c > k) {
+        T sdot = A[k][c];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) if (r > k) sdot += A[r][k] * A[r][c];
+        sdot *= tk;
+        A[k][c] -= sdot;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) if (r > k) A[r][c] -= sdot * A[r][k];
+      }
+    }
+  }
+  R[0] = A[0][0]; R[1] = A[0][1]; R[2] = A[0][2]; R[3] = A[1][1]; R[4] = A[1][2]; R[5] = A[2][2];
+  pm = pmv[0] | (pmv[1] << 2) | (pmv[2] << 4);
+  // top 3 rows of the thin Q: E = H0 H1 H2 [I3; 0], H_k = I - tau_k v_k v_k^T, v_k = (0.., 1 at row k, A[r][k] below)
+  T E[6][3] = {{T(1), T(0), T(0)}, {T(0), T(1), T(0)}, {T(0), T(0), T(1)}, {T(0), T(0), T(0)}, {T(0), T(0), T(0)}, {T(0), T(0), T(0)}};
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      T sdot = E[k][c];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) if (r > k) sdot += A[r][k] * E[r][c];
+      sdot *= tau[k];
+      E[k][c] -= sdot;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) if (r > k) E[r][c] -= sdot * A[r][k];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Q11[r][c] = E[r][c];
+}
+
+template <class T>
+__global__ void __launch_bounds__(TILE, 4) k_moreqr_stage2(const T lambda, int nunits, const int* __restrict__ unit_obs, const int* __restrict__ seg,
+                                                           const int* __restrict__ slot, const int* __restrict__ point, const T* __restrict__ Jrec,
+                                                           const T* __restrict__ Ptrec0, T* __restrict__ Prec, T* __restrict__ Drec, T* __restrict__ Ptrec) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int EPC = RecGeom<T>::EPC, CPR = RecGeom<T>::CPR, SR = RecGeom<T>::SREC;
+  constexpr int RPI = 32 / CPR, NQ = 32 / RPI;
+  const int lane = threadIdx.x & 31, u = blockIdx.x * (TILE / 32) + (threadIdx.x >> 5);
+  if (u >= nunits) return;
+  extern __shared__ __align__(16) unsigned char mq_smem_raw[];
+  T* const my = reinterpret_cast<T*>(mq_smem_raw) + (size_t)(threadIdx.x >> 5) * 32 * SR;
+  const int2 uo = __ldg(reinterpret_cast<const int2*>(unit_obs) + u);
+  const int o0 = uo.x, un = uo.y;
+  const bool act = lane < un;
+  const int o = o0 + (act ? lane : 0);
+  const int rsub = lane / CPR, part = lane - rsub * CPR;
+  const bool cpl = lane < RPI * CPR;
+  // the unit's J records are contiguous: staged with coalesced cp.async (lane = (record, 16-byte chunk))
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int r = RPI * q + rsub;
+    if (cpl && r < un) rec_cp16(my + r * SR + part * EPC, Jrec + (size_t)(o0 + r) * REC + part * EPC);
+  }
+  rec_commit();
+  const int pj = __ldg(point + o), sg = __ldg(seg + o);
+  const size_t sl = (size_t)__ldg(slot + o);
+  const int i = act ? (sg & 0xff) : 0;
+  T R0[6], c0[3], G[3], pf, z0_, z1_, z2_;
+  {
+    const T* q = Ptrec0 + (size_t)pj * PREC;
+    load4(q, R0[0], R0[1], R0[2], R0[3]);
+    load4(q + 4, R0[4], R0[5], c0[0], c0[1]);
+    load4(q + 8, c0[2], G[0], G[1], G[2]);
+    load4(q + 12, pf, z0_, z1_, z2_);
+  }
+  T R[6], Q11[3][3]; int pm1 = 0;
+  moreqr_inner_qr<T>(R0, tsqrt(lambda), R, pm1, Q11);
+  const int pm0 = (int)pf;
+  // dx_j (original order) = P0 P' z: column a of R' is column pm1[a] of R0, i.e. original column pm0[pm1[a]]
+  int pm = 0;
+#pragma unroll
+  for (int a2 = 0; a2 < 3; ++a2) { const int m = (pm1 >> (2 * a2)) & 3; pm |= ((pm0 >> (2 * m)) & 3) << (2 * a2); }
+  T cq[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) cq[k] = Q11[0][k] * c0[0] + Q11[1][k] * c0[1] + Q11[2][k] * c0[2];
+  rec_wait<0>();
+  __syncwarp();
+  T jr[REC];
+  lds_rec<0, REC>(my + lane * SR, jr);
+  __syncwarp();
+  T x[2][3];
+#pragma unroll
+  for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) x[a2][k] = jr[18 + 3 * a2] * Q11[0][k] + jr[18 + 3 * a2 + 1] * Q11[1][k] + jr[18 + 3 * a2 + 2] * Q11[2][k];
+  const T e0 = jr[24], e1 = jr[25];
+  T rec[REC];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int b = 0; b < 9; ++b) rec[9 * k + b] = x[0][k] * jr[b] + x[1][k] * jr[9 + b];
+  rec[27] = T(0);
+  store_rec(my + lane * SR, rec);
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int r = RPI * q + rsub;
+    if (cpl && r < un)
+      *reinterpret_cast<int4*>(Prec + (size_t)(o0 + r) * REC + part * EPC) = *reinterpret_cast<const int4*>(my + r * SR + part * EPC);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int b = 0; b < 18; ++b) rec[b] = jr[b];
+  fill_drec_tail<T>(rec, x[0][0], x[0][1], x[0][2], x[1][0], x[1][1], x[1][2], cq[0], cq[1], cq[2], e0, e1);
+  store_rec(my + lane * SR, rec);
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int r = RPI * q + rsub;
+    const size_t slr = (size_t)__shfl_sync(FULL, (int)sl, r & 31);
+    if (cpl && r < un)
+      *reinterpret_cast<int4*>(Drec + slr * REC + part * EPC) = *reinterpret_cast<const int4*>(my + r * SR + part * EPC);
+  }
+  if (act && i == 0) {
+    T* q = Ptrec + (size_t)pj * PREC;
+    store4(q, R[0], R[1], R[2], R[3]);
+    store4(q + 4, R[4], R[5], cq[0], cq[1]);
+    store4(q + 8, cq[2], G[0], G[1], G[2]);
+    store4(q + 12, (T)pm, T(0), T(0), T(0));
   }
 }
 

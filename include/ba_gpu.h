@@ -67,8 +67,10 @@ int ba_eval(ba_handle* h, double* energy);
 
 /* ≙ functor.df(x, J); JtRes; column norms (QRChol.h:264-280; More.h:268-291; Cholesky.h:247-265).
  * The Jacobian is never materialised for QRKIT/QRCHOL/CHOLESKY (re-evaluated inside ba_compute); for
- * MOREQR the point blocks are currently re-factored per trial with the damping rows in place (same step as the
- * reference's two-stage scheme, More.h:288-348, up to rounding; no stage-1 state is kept). max_colnorm2 = max_c |J(:,c)|^2,
+ * MOREQR this also runs stage 1 (QR of the UN-damped point blocks, More.h:288-291: R0_j, Q0, c0 kept per point /
+ * observation), so that every lambda trial of ba_compute only re-triangularises the 6x3 blocks [R0_j; sqrt(lambda) I3]
+ * (More.h:293-348). Points with more than 32 observations, and inputs with single-observation points, re-factor the
+ * damped block per trial instead (same step up to rounding). max_colnorm2 = max_c |J(:,c)|^2,
  * max_colnorm = its square root (blueNorm rule of More.h:277); either may be NULL to skip the pass. */
 int ba_linearize(ba_handle* h, double* energy, double* max_colnorm2, double* max_colnorm);
 

@@ -371,3 +371,39 @@ def test_singular_reduced_system_is_reported():
     with pytest.raises(solver.BAError):
         s.solve_try()
     s.close()
+
+
+def test_moreqr_two_stage_scheme(p21):
+    """MOREQR (BacktrackLevMarqMore.h:288-348): the un-damped point blocks are factored once per linearisation
+    (stage 1), every lambda trial only re-triangularises [R0_j; sqrt(lambda) I3] (stage 2). Same step as re-factoring
+    the damped blocks per trial (BA_MOREQR_TWOSTAGE=0) and as the oracle's own two-stage restatement, for several
+    lambdas out of ONE linearisation; stage 1 is redone after an accepted step."""
+    import os
+    o = Oracle(p21)
+    eo, cn2o, cno = o.linearize()
+    o.moreqr_outer()
+    s2 = solver.GpuSolver(p21, "MOREQR")
+    os.environ["BA_MOREQR_TWOSTAGE"] = "0"
+    try:
+        s1 = solver.GpuSolver(p21, "MOREQR")
+    finally:
+        os.environ.pop("BA_MOREQR_TWOSTAGE")
+    s1.linearize(); s2.linearize()
+    l0 = s2.launches()
+    for lam in (1e-6 * cno, 1e-2, 1e-4):
+        ok, dxo = o.step(solver.MOREQR, lam)
+        s1.compute(lam); d1, _, e1 = s1.solve_try(); s1.reject()
+        s2.compute(lam); d2, _, e2 = s2.solve_try()
+        tol = max(1e-9, 1e-3 * min(7e9 / lam, 1e16) * 2.2e-16)
+        assert relv(e2, o.energy_at(dxo)) < tol and relv(e2, e1) < tol, (lam, e2, e1)
+        assert rel(s2.dx(), dxo) < 1e3 * tol and rel(s2.dx(), s1.dx()) < 1e3 * tol
+        if lam != 1e-4:
+            s2.reject()
+    s2.accept()                      # new state: the next linearisation must rebuild stage 1
+    s2.linearize()
+    o.set_state(*s2.get_state()); o.linearize(); o.moreqr_outer()
+    lam = 1e-3
+    ok, dxo = o.step(solver.MOREQR, lam)
+    s2.compute(lam); _, _, e2 = s2.solve_try()
+    assert relv(e2, o.energy_at(dxo)) < 1e-8
+    s1.close(); s2.close()
