@@ -23,7 +23,7 @@ SYMBOLS = [
     "ba_compute", "ba_solve_try", "ba_accept", "ba_reject", "ba_get_dx", "ba_get_residuals",
     "ba_get_reduced_system", "ba_keep_reduced_system", "ba_get_jacobian", "ba_launch_count",
     "ba_stage_ms", "ba_set_profiling", "ba_timer_start", "ba_timer_stop", "ba_debug_counters",
-    "ba_debug_band_solve", "ba_numeric_status", "ba_set_strict_numeric",
+    "ba_debug_band_solve", "ba_numeric_status", "ba_set_strict_numeric", "ba_debug_counters_n",
 ]
 
 _LIB = None
@@ -81,6 +81,7 @@ def lib():
     L.ba_stage_ms.argtypes = [vp, dp]
     L.ba_set_profiling.argtypes = [vp, C.c_int]
     L.ba_debug_counters.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.ba_debug_counters_n.argtypes = [vp, C.POINTER(C.c_longlong), C.c_int]
     L.ba_debug_band_solve.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp]
     L.ba_timer_start.argtypes = [vp]
     L.ba_numeric_status.argtypes = [vp, ip]

@@ -246,7 +246,7 @@ struct ba_handle {
   virtual int set_bandwidth(int) = 0;
   virtual int timer_start() = 0;
   virtual int timer_stop(double*) = 0;
-  virtual int debug_counters(long long*) = 0;
+  virtual int debug_counters(long long*, int) = 0;
   virtual int debug_band_solve(int, int, const double*, const double*, double*) = 0;
   int bw = 0;
   int numeric_info = 0;        // last ba_solve_try: 0 ok, > 0 zero/NaN pivot at that (1-based) row of the reduced system, -1 non-finite step
@@ -287,7 +287,7 @@ struct Impl : ba_handle {
   int cluster_size = 16;  // non-portable size; falls back to 8 when 16 CTAs of this footprint cannot be co-scheduled
   bool solved_in_factor = false;
   int ldlt_roww = 6;  // row-tile warps per chain CTA of the cluster LDLT (BA_LDLT_ROWW=3|6)
-  bool ldlt_v2 = true; // forward elimination of the two-sided scheme by the owner-computes kernel (BA_LDLT_V2=0: first generation)
+  bool ldlt_v2 = false; // BA_LDLT_V2=1: forward elimination of the two-sided scheme by the owner-computes kernel (ba_ldlt2.cuh; correct, not yet faster)
   DevBuf<double> d_partials, d_scal;
   DevBuf<long long> d_dbg;
   double* h_scal = nullptr;  // pinned
@@ -442,7 +442,7 @@ struct Impl : ba_handle {
     CK(d_X.alloc(3 * (size_t)M)); CK(d_X_test.alloc(3 * (size_t)M));
     CK(d_dx_pt.alloc(3 * (size_t)M)); CK(d_dx_cam.alloc(9 * (size_t)N));
     const size_t npart = std::max<size_t>(3 * (size_t)(ntiles + nhuge), (size_t)(K + 255) / 256);
-    CK(d_partials.alloc(npart)); CK(d_scal.alloc(16)); CK(d_dbg.alloc(16)); CK(cudaMemset(d_dbg.p, 0, 16 * sizeof(long long)));
+    CK(d_partials.alloc(npart)); CK(d_scal.alloc(16)); CK(d_dbg.alloc(256)); CK(cudaMemset(d_dbg.p, 0, 256 * sizeof(long long)));
     CK(cudaMallocHost(&h_scal, 16 * sizeof(double)));
     CK(cudaMemcpyAsync(d_view.p, view, K * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(d_point.p, point, K * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -1043,9 +1043,10 @@ struct Impl : ba_handle {
     return BA_OK;
   }
 
-  int debug_counters(long long* out) override {
+  int debug_counters(long long* out, int count) override {
     CK(cudaSetDevice(device));
-    CK(cudaMemcpy(out, d_dbg.p, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (count < 1 || count > 256) return fail(BA_ERR_ARG, "debug counters: 1..256");
+    CK(cudaMemcpy(out, d_dbg.p, count * sizeof(long long), cudaMemcpyDeviceToHost));
     return BA_OK;
   }
 
@@ -1133,7 +1134,8 @@ int ba_get_jacobian(ba_handle* h, double* Jc, double* Jp) { H_CHECK; return h->g
 int ba_launch_count(ba_handle* h, long long* launches) { H_CHECK; *launches = h->launches; return BA_OK; }
 int ba_stage_ms(ba_handle* h, double* s) { H_CHECK; for (int i = 0; i < 8; ++i) s[i] = h->stage_ms[i]; return BA_OK; }
 int ba_set_profiling(ba_handle* h, int enable) { H_CHECK; h->profiling = enable != 0; return BA_OK; }
-int ba_debug_counters(ba_handle* h, long long* out16) { H_CHECK; return h->debug_counters(out16); }
+int ba_debug_counters(ba_handle* h, long long* out16) { H_CHECK; return h->debug_counters(out16, 16); }
+int ba_debug_counters_n(ba_handle* h, long long* out, int count) { H_CHECK; return h->debug_counters(out, count); }
 int ba_timer_start(ba_handle* h) { H_CHECK; return h->timer_start(); }
 int ba_debug_band_solve(ba_handle* h, int n, int kd, const double* S, const double* g, double* y) { H_CHECK; return h->debug_band_solve(n, kd, S, g, y); }
 int ba_timer_stop(ba_handle* h, double* ms) { H_CHECK; return h->timer_stop(ms); }

@@ -43,6 +43,7 @@ struct Ldlt2Smem {
   int snb[8];                                    // slots of that class
   long long tc[16];                              // phase cycle counters (-DBA_L2_TICKS)
   int chain_done;                                // this CTA's chain warp published panel p: p + 1 (warp 0 -> warp 4)
+  int prio_cnt;                                  // column tiles that have received their last update (running count, all panels)
   int panel_ready;                               // W_p, D_p, z_p of panel p are in global memory: p + 1 (written by the diagonal owner's warp 4 into the four CTAs that own column p)
 };
 
@@ -50,6 +51,10 @@ struct Ldlt2Smem {
 __device__ __forceinline__ int l2_swz(int r, int c) { return r * NB + ((((c >> 1) ^ ((r & 3) << 1)) << 1) | (c & 1)); }
 __device__ __forceinline__ void l2_st_release_cluster(int* p, int v) { asm volatile("st.release.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ int l2_ld_acquire_cluster(const int* p) { int v; asm volatile("ld.acquire.cluster.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void l2_red_release_cta(int* p, int v) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("red.release.cta.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void l2_bar_update(const int nthr) { asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); }
 
 // acc (accumulator order, e = 2 (4 mi + ni) + h <-> row 8 mi + lane/4, column 8 ni + 2 (lane%4) + h) += A (ms B)^T.
@@ -283,8 +288,14 @@ __device__ __forceinline__ void l2_warp_w32(double (&a)[NB], const PanelSmem<dou
 // P.y is used as scratch for z_k = L_kk^-1 g_k on the eliminated rows.
 #ifdef BA_L2_TICKS
 #define L2TICK(i) { if (lane == 0) { const long long t1_ = clock64(); sm.tc[i] += t1_ - tprev; tprev = t1_; } __syncwarp(); }
+// timeline of ONE iteration (k == BA_L2_EVK) of cluster 0: event e of warp w of CTA `rank`, cycles since that CTA left the barrier
+#ifndef BA_L2_EVK
+#define BA_L2_EVK 101
+#endif
+#define L2EV(e) { if (dbg && lane == 0 && k == BA_L2_EVK && blockIdx.x < 16 && (warp == 0 || warp == 1 || warp == 4)) dbg[16 + rank * 12 + (warp == 0 ? 0 : warp == 1 ? 4 : 8) + (e)] = clock64() - tev0; }
 #else
 #define L2TICK(i) {}
+#define L2EV(e) {}
 #endif
 __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<double> job, long long* __restrict__ dbg) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
   if (tid < 2 * NB) { sm.pn.sCol[0][NB + (tid & 31)] = 0.0; sm.pn.sCol[1][NB + (tid & 31)] = 0.0; }
   if (tid < 16) sm.tc[tid] = 0;
   if (tid == 0) {
-    sm.pn.progress = 0; sm.chain_done = 0; sm.panel_ready = 0;
+    sm.pn.progress = 0; sm.chain_done = 0; sm.panel_ready = 0; sm.prio_cnt = 0;
     const int d0 = (r - c + 4) & 3;
     int b = 0;
     for (int dq = 0; dq < 8; ++dq) {
@@ -356,70 +367,103 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
     __syncwarp();
   };
 
-  // ---- T(k): L(i, k) = T(i, k) W_k^T D_k^-1 on the CTAs that own column k, once the chain has published panel k. All eight
-  // warps; unit q = (tile q / 2, half q % 2), warp w takes the units w and w + 8.
-  auto solve_column = [&](const int k) {
+  // ---- T(k): L(i, k) = T(i, k) W_k^T D_k^-1 on the CTAs that own column k, once the chain has published panel k (flag)
+  // and the column's tiles have received their last update (prio_cnt >= prio_target). Every warp works on its own: unit
+  // q = (row tile q / 2, half q % 2) goes to participating warp q % nw; the row operand comes straight from the tile's
+  // slot (accumulator order, read in fragment order), W_k / D_k / z_k straight from L2, the result straight to the band
+  // storage: no shared scratch, no CTA barrier, so the rest of the window update goes on around it.
+  auto solve_column = [&](const int k, const int wi, const int nw, const int prio_target) {
     const int k0 = k * NB, hi = min(k + bt, nt - 1);
     const int ia0 = (k + 1) + ((r - (k + 1)) & 3);
-    __syncthreads();                                   // this CTA's window updates (and its chain warps) are done
-    if (lane == 0) { while (l2_ld_acquire_cluster(&sm.panel_ready) < k + 1) {} }
+    const int ntile = (hi >= ia0) ? ((hi - ia0) >> 2) + 1 : 0;
+    if (wi >= 2 * ntile) return;
+    if (lane == 0) {
+      while (l2_ld_acquire_cluster(&sm.panel_ready) < k + 1) {}
+      while (ld_acquire_cta(&sm.prio_cnt) < prio_target) {}
+    }
     __syncwarp();
     (void)l2_ld_acquire_cluster(&sm.panel_ready);
-    {
-      for (int q = tid; q < NB * NB / 2; q += CL_THREADS) {   // W_k -> opB[0]
-        const int rr = q >> 4, ch = q & 15;
-        cp_async16(sm.opB[0] + rr * NB + ((ch ^ ((rr & 3) << 1)) << 1), Wbuf + (size_t)k * NB * NB + rr * NB + 2 * ch);
+    (void)ld_acquire_cta(&sm.prio_cnt);
+    const int lr = lane >> 2, lc = lane & 3;
+    const double* Wk = Wbuf + (size_t)k * NB * NB;
+    for (int q = wi; q < 2 * ntile; q += nw) {
+      const int t = q >> 1, h = q & 1, i = ia0 + 4 * t;
+      // column operands: W_k (lower triangular), 1 / D_k and z_k of this lane's eight columns
+      double bf[4][NB / 4], invd[8], zk[8];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int kk = 0; kk < NB / 4; ++kk) bf[ni][kk] = (kk <= 2 * ni + 1) ? Wk[(ni * 8 + lr) * NB + kk * 4 + lc] : 0.0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int col = (e >> 1) * 8 + 2 * lc + (e & 1);
+        invd[e] = dvec[k0 + col];
+        zk[e] = *((k0 + col < n) ? zscr + k0 + col : zp);
       }
-      cp_async_commit();
-      if (tid < NB) { const double d = dvec[k0 + tid]; sm.sinvdT[tid] = pivot_rcp(d); sm.szT[tid] = *((k0 + tid < n) ? zscr + k0 + tid : zp); }
-      const int ntile = (hi >= ia0) ? ((hi - ia0) >> 2) + 1 : 0;
-      const int lr = lane >> 2, lc = lane & 3;
-      double rold[2][2];
+      double rold[2];
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const int q = warp + 8 * v;
-        rold[v][0] = rold[v][1] = 0.0;
-        if (q < 2 * ntile) {
-          const int t = q >> 1, h = q & 1, i = ia0 + 4 * t;
-          double acc[16];
-          if (k > max(0, i - bt)) l2_load_slot_half(slot_of(i, k), lane, h, acc);   // received at least one update: lives in its slot
-          else l2_load_tile_half(A, i, k, lane, h, acc);
-          l2_acc_to_smem_half(sm.opA[t], lane, h, acc);
+      for (int ml = 0; ml < 2; ++ml) { const int gi = i * NB + (2 * h + ml) * 8 + lr; rold[ml] = *((lc == 0 && gi < n) ? rhs + gi : zp); }
+      // row operand in fragment order: A(8 (2h + ml) + lr, 4 kk + lc)
+      double af[2][NB / 4];
+      if (k > max(0, i - bt)) {                                   // received at least one update: lives in its slot
+        const double* sl = slot_of(i, k);
 #pragma unroll
-          for (int ml = 0; ml < 2; ++ml) { const int gi = i * NB + (2 * h + ml) * 8 + lr; rold[v][ml] = *((lc == 0 && gi < n) ? rhs + gi : zp); }
-        }
-      }
-      cp_async_wait_all();
-      __syncthreads();
+        for (int ml = 0; ml < 2; ++ml)
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const int q = warp + 8 * v;
-        if (q < 2 * ntile) {
-          const int t = q >> 1, h = q & 1, i = ia0 + 4 * t;
-          double x[16];
+          for (int kk = 0; kk < NB / 4; ++kk)
+            af[ml][kk] = sl[(4 * (2 * h + ml) + (kk >> 1)) * 64 + (lr * 4 + (kk & 1) * 2 + (lc >> 1)) * 2 + (lc & 1)];
+      } else {
+        const double* tp = A.v + (size_t)(i * NB) * lds + k0;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) x[e] = 0.0;
-          l2_mma_half_w(sm.opA[t], sm.opB[0], lane, h, x);
-          double part[2] = {0.0, 0.0};
+        for (int ml = 0; ml < 2; ++ml)
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int col = ((e >> 1) & 3) * 8 + 2 * lc + (e & 1);
-            x[e] *= sm.sinvdT[col];
-            part[e >> 3] += x[e] * sm.szT[col];
+          for (int kk = 0; kk < NB / 4; ++kk) {
+            const int rr = (2 * h + ml) * 8 + lr, cc = kk * 4 + lc, gi = i * NB + rr, gj = k0 + cc;
+            const bool ok = gi < n && gj <= gi && gi - gj <= kd;
+            af[ml][kk] = *(ok ? tp + rr * lds + cc : zp);
           }
-#pragma unroll
-          for (int ml = 0; ml < 2; ++ml) {
-            part[ml] += __shfl_xor_sync(FULL, part[ml], 1);
-            part[ml] += __shfl_xor_sync(FULL, part[ml], 2);
-            const int gi = i * NB + (2 * h + ml) * 8 + lr;
-            if (lc == 0 && gi < n) rhs[gi] = rold[v][ml] - part[ml];
-          }
-          __syncwarp();
-          l2_acc_to_smem_half(sm.opA[t], lane, h, x);
-          __syncwarp();
-          l2_smem_to_tile_half(sm.opA[t], A, i, k0, lane, h);
-        }
       }
+      double x[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) x[e] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < NB / 4; ++kk)
+#pragma unroll
+        for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            if (kk > 2 * ni + 1) continue;
+            dmma884(x[2 * (4 * ml + ni)], x[2 * (4 * ml + ni) + 1], af[ml][kk], bf[ni][kk]);
+          }
+      double part[2] = {0.0, 0.0};
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int ce = ((e >> 1) & 3) * 2 + (e & 1);                // index into this lane's eight columns
+        x[e] *= pivot_rcp(invd[ce]);
+        part[e >> 3] += x[e] * zk[ce];
+      }
+#pragma unroll
+      for (int ml = 0; ml < 2; ++ml) {
+        part[ml] += __shfl_xor_sync(FULL, part[ml], 1);
+        part[ml] += __shfl_xor_sync(FULL, part[ml], 2);
+        const int gi = i * NB + (2 * h + ml) * 8 + lr;
+        if (lc == 0 && gi < n) rhs[gi] = rold[ml] - part[ml];
+      }
+      double* tp = A.v + (size_t)(i * NB) * lds + k0;
+      const bool interior = (i * NB + NB - 1 < n) && (i * NB + NB - 1 - k0 <= kd);
+#pragma unroll
+      for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int rr = (2 * h + ml) * 8 + lr, cc = ni * 8 + 2 * lc;
+          if (interior) {
+            *reinterpret_cast<double2*>(tp + rr * lds + cc) = make_double2(x[2 * (4 * ml + ni)], x[2 * (4 * ml + ni) + 1]);
+          } else {
+            const int gi = i * NB + rr, gj = k0 + cc;
+            if (gi < n && gi - gj <= kd) tp[rr * lds + cc] = x[2 * (4 * ml + ni)];
+            if (gi < n && gi - gj - 1 <= kd) tp[rr * lds + cc + 1] = x[2 * (4 * ml + ni) + 1];
+          }
+        }
     }
   };
 
@@ -440,19 +484,25 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
       form_w(0);
     }
   }
-  if (np_fwd > 0 && c == 0) solve_column(0);
+  if (np_fwd > 0 && c == 0) solve_column(0, warp, CL_WARPS, 0);
   cluster.sync();
 
+  int prio_target = 0;   // running number of column tiles this CTA has to finish before it may solve the column (same on every warp)
   for (int k = 0; k < np_fwd; ++k) {
     const int k0 = k * NB, hi = min(k + bt, nt - 1);
     const int ia0 = (k + 1) + ((r - (k + 1)) & 3);     // first tile row >= k+1 owned by this CTA row
     const int jb0 = (k + 1) + ((c - (k + 1)) & 3);     // first tile column >= k+1 owned by this CTA column
+#ifdef BA_L2_TICKS
+    const long long tev0 = clock64();
+#endif
     // ======================= U(k): the window receives panel k's update; F(k+1) on the owner of the next diagonal tile
     const bool prio = (k + 1 < np_fwd);                 // the tile (k+1, k+1) goes to the chain warp
     const bool last = (k == np_fwd - 1);                // last panel: updated tiles also return to the band storage
     const bool chain_here = prio && rank == diag_owner(k + 1);   // warps 0 and 4 of this CTA run the chain of panel k+1
     const int nuw = chain_here ? L2_UW : CL_WARPS;               // otherwise they update like everybody else
     const int uw = chain_here ? (upd_warp ? u : -1) : warp;
+    const bool col_cta = prio && c == ((k + 1) & 3);             // this CTA owns tiles of column k+1: it solves them (T(k+1))
+    if (col_cta) { for (int i = (k + 2) + ((r - (k + 2)) & 3); i <= hi; i += 4) ++prio_target; }
     if (uw >= 0) {
       const int nthr = 32 * nuw, utx = 32 * uw + lane;
       for (int t = 0, i = ia0; i <= hi; ++t, i += 4) {
@@ -470,14 +520,22 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
       for (int t = 0, j = jb0; j <= hi; ++t, j += 4) l2_fix_tile(sm.opB[t], A, j, k0, utx, nthr);
       l2_bar_update(nthr);
       if (warp == 1) L2TICK(6)
+      L2EV(0)
       double ms[NB / 4];
 #pragma unroll
       for (int kk = 0; kk < NB / 4; ++kk) ms[kk] = -sm.sdU[kk * 4 + (lane & 3)];
+      // Column k+1 comes first (jb0 = k+1 on its owners); every such tile bumps prio_cnt when its update is stored, and a
+      // warp solves its share of the column (T(k+1)) as soon as the chain's flag is up, between two tile updates.
+      bool t_pending = col_cta;
       int t = 0;
       for (int jt = 0, j = jb0; j <= hi; ++jt, j += 4) {
         const int i0 = j + ((r - j) & 3);
         for (int i = i0; i <= hi; i += 4) {
           if (prio && i == k + 1 && j == k + 1) continue;
+          if (t_pending && j > k + 1 && l2_ld_acquire_cluster(&sm.panel_ready) >= k + 2 && ld_acquire_cta(&sm.prio_cnt) >= prio_target) {
+            solve_column(k + 1, uw, nuw, prio_target);
+            t_pending = false;
+          }
           if (t % nuw == uw) {
             double acc[32];
             double* s = slot_of(i, j);
@@ -486,11 +544,16 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
             if (i == j) l2_mma<1>(sm.opA[(i - ia0) >> 2], sm.opB[jt], ms, lane, acc);
             else l2_mma<0>(sm.opA[(i - ia0) >> 2], sm.opB[jt], ms, lane, acc);
             if (last) l2_store_tile(A, i, j, lane, acc); else l2_store_slot(s, lane, acc);
+            if (col_cta && j == k + 1) { __syncwarp(); if (lane == 0) l2_red_release_cta(&sm.prio_cnt, 1); }
           }
           ++t;
         }
       }
       if (warp == 1) L2TICK(7)
+      L2EV(1)
+      if (t_pending) solve_column(k + 1, uw, nuw, prio_target);
+      L2EV(2)
+      if (warp == 1) L2TICK(5)
     } else {   // chain_here: warps 0 and 4
       const int k1 = k + 1;
       if (warp == 0) {
@@ -506,6 +569,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
         l2_fix_tile(sm.opA[0], A, k1, k0, lane, 32);
         __syncwarp();
         L2TICK(0)
+        L2EV(0)
         l2_mma<1>(sm.opA[0], sm.opA[0], ms, lane, acc);
         L2TICK(1)
         // accumulator order -> one row per lane through the (idle) L_kk^T buffer, rows rotated by their index
@@ -528,16 +592,18 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
         }
         __syncwarp();
         L2TICK(2)
+        L2EV(1)
         factor_publish(a, z, k1);
         L2TICK(3)
+        L2EV(2)
       } else {  // warp 4
         form_w(k1);
+        L2EV(0)
       }
     }
     if (warp == 1) L2TICK(8)
-    if (prio && c == ((k + 1) & 3)) solve_column(k + 1);
-    if (warp == 1) L2TICK(5)
     cluster.sync();
+    L2EV(3)
     if (warp == 1) L2TICK(9)
     if (warp == 0) L2TICK(12)
   }
@@ -546,5 +612,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
 #endif
 }
 #undef L2TICK
+#undef L2EV
 
 }  // namespace ba

@@ -178,6 +178,11 @@ class GpuSolver:
         self._ck(self._L.ba_debug_counters(self._h, v))
         return list(v)
 
+    def debug_counters_n(self, n=256):
+        v = (C.c_longlong * n)()
+        self._ck(self._L.ba_debug_counters_n(self._h, v, n))
+        return list(v)
+
     def debug_band_solve(self, S, g, kd):
         S = np.ascontiguousarray(S, dtype=np.float64)
         g = np.ascontiguousarray(g, dtype=np.float64)

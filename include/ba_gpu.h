@@ -119,6 +119,7 @@ int ba_stage_ms(ba_handle* h, double* stage_ms8);
 int ba_set_profiling(ba_handle* h, int enable);
 /* Debug: 16 device cycle counters of the last dense-stage kernel (phase split; see csrc/ba_dense.cuh). */
 int ba_debug_counters(ba_handle* h, long long* out16);
+int ba_debug_counters_n(ba_handle* h, long long* out, int count);  /* up to 256 (tick builds: per-CTA timelines) */
 /* Test hook (not on the hot path): factor + solve S y = g for an arbitrary symmetric band matrix (S dense
  * row-major n x n, half-bandwidth kd) with this handle's reduced-camera-block solver (LDL^T or QR by variant). */
 int ba_debug_band_solve(ba_handle* h, int n, int kd, const double* S, const double* g, double* y);

@@ -17,3 +17,10 @@ npan = 253.0
 ghz = 1.965
 for n, v in zip(names, c):
     if n != "-": print(f"{n:24s} {v / npan / ghz / 1e3:8.3f} us/panel (CTA 0 is diagonal owner / column owner every 4th panel)")
+
+ev = s.debug_counters_n(16 + 16 * 12)[16:]
+print("timeline of iteration 101 (us after the CTA left the cluster barrier); chain owner = CTA 10, column CTAs = 2, 6, 10, 14")
+print("CTA | warp0: (chain) staged / stg->regs / published | warp1: staged+barrier / window done / column solved | warp4: staged(or W done) / window done / column solved | all: barrier passed (warp0, warp1, warp4)")
+for rk in range(16):
+    v = [x / 1.965e3 for x in ev[rk * 12:(rk + 1) * 12]]
+    print(f"{rk:3d} | " + " ".join(f"{x:6.2f}" for x in v[0:3]) + " | " + " ".join(f"{x:6.2f}" for x in v[4:7]) + " | " + " ".join(f"{x:6.2f}" for x in v[8:11]) + f" | {v[3]:6.2f} {v[7]:6.2f} {v[11]:6.2f}")
