@@ -278,6 +278,11 @@ struct Impl : ba_handle {
   DevBuf<T> d_P, d_D, d_Pt;  // per-observation (P, D) / per-point records written by k_point_factor*
   DevBuf<T> d_J, d_Pt0;      // MOREQR stage 1 (un-damped point QR, once per outer iteration): J records, point records
   bool two_stage = false, stage1_valid = false;
+  // QRKIT / MOREQR right block: LDL^T of S + corrected semi-normal refinement through J2bot (k_csne_*), or (BA_QR_HOUSEHOLDER=1)
+  // the Householder QR of the square S of round 1
+  bool qr_csne = false; int csne_steps = 1, nlong = 0;
+  DevBuf<T> d_keepS, d_u, d_delta;
+  DevBuf<int> d_long_pt;
   int nblocks = 0, gather_grid = 0;
   DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g | gJ */, d_keep, d_dvec, d_tmp;
   DevBuf<T> d_qr;  // general band copy for the Householder QR of S
@@ -325,6 +330,7 @@ struct Impl : ba_handle {
     CK(d_red.alloc(red_count + 2 * (size_t)n));
     CK(d_dvec.alloc((size_t)n + NB));  // D is read/written in whole 32-wide panels
     if (keep_reduced) CK(d_keep.alloc(red_count + n));
+    if (qr_csne) { CK(d_keepS.alloc(red_count)); CK(d_delta.alloc(n)); }
     d_qr.free();
     return BA_OK;
   }
@@ -383,6 +389,13 @@ struct Impl : ba_handle {
       j = j1;
     }
     nunits = (int)unit_pt.size() / 2; nbig = (int)big_pt.size() / 2;
+    std::vector<int> long_pt;
+    for (int j = 0; j < M; ++j) if (pt_start[j + 1] - pt_start[j] > 32) long_pt.push_back(j);
+    nlong = (int)long_pt.size();
+    // double only: the refinement needs cond(S) eps < 1, which never holds in float on BA problems (measured: it makes the
+    // float step worse); the float build keeps the Householder QR of S
+    qr_csne = (variant == BA_QRKIT || variant == BA_MOREQR) && sizeof(T) == 8 && !std::getenv("BA_QR_HOUSEHOLDER");
+    if (const char* rs = std::getenv("BA_QR_REFINE")) csne_steps = std::max(0, std::min(4, atoi(rs)));
     // MOREQR two-stage scheme (More.h:288-348) for the points handled by the warp kernel; a point with a single
     // observation has a rank-2 un-damped block (2 x 3), which the segmented Householder does not cover: such inputs
     // (none in the BAL files: every point has >= 2 observations) fall back to re-factoring the damped blocks per trial
@@ -460,6 +473,11 @@ struct Impl : ba_handle {
     CK(d_pairs.alloc(pairs.size()));
     CK(d_P.alloc((size_t)K * REC)); CK(d_D.alloc((size_t)K * REC)); CK(d_Pt.alloc((size_t)M * PREC));
     if (two_stage) { CK(d_J.alloc((size_t)K * REC)); CK(d_Pt0.alloc((size_t)M * PREC)); }
+    if (qr_csne) {
+      CK(d_u.alloc(2 * (size_t)K)); CK(d_long_pt.alloc(long_pt.size() + 1));
+      if (nlong) CK(cudaMemcpyAsync(d_long_pt.p, long_pt.data(), nlong * sizeof(int), cudaMemcpyHostToDevice, stream));
+      CK(cudaStreamSynchronize(stream));
+    }
     CK(cudaMemcpyAsync(d_slot.p, slot.data(), K * sizeof(int), cudaMemcpyHostToDevice, stream));
     {
       std::vector<int> inv(K);   // observation stored at each camera-major slot (column norms of the camera columns)
@@ -709,6 +727,7 @@ struct Impl : ba_handle {
       if (d_keep.n < red_count + n) CK(d_keep.alloc(red_count + n));
       CK(cudaMemcpyAsync(d_keep.p, d_red.p, (red_count + n) * sizeof(T), cudaMemcpyDeviceToDevice, stream));
     }
+    if (qr_csne && csne_steps > 0) CK(cudaMemcpyAsync(d_keepS.p, d_red.p, red_count * sizeof(T), cudaMemcpyDeviceToDevice, stream));  // S again for the refinement solve
     mark(3);
     { int rc = factor_reduced(); if (rc) return rc; }
     mark(4);
@@ -724,7 +743,7 @@ struct Impl : ba_handle {
 
   // factorisation of the reduced camera block in d_red (LDL^T or Householder QR of S)
   int factor_reduced() {
-    if (variant == BA_QRCHOL || variant == BA_CHOLESKY) {
+    if (variant == BA_QRCHOL || variant == BA_CHOLESKY || qr_csne) {
       CK(cudaMemsetAsync(d_info.p, 0, sizeof(int), stream));
       BandMat<T> A = band();
       const int nt = (n + NB - 1) / NB, bt = (kd + NB - 1) / NB;
@@ -858,7 +877,7 @@ struct Impl : ba_handle {
 
   // dx_cam = -S^-1 g from the factor above
   int solve_reduced() {
-    if (variant == BA_QRCHOL || variant == BA_CHOLESKY) {
+    if (variant == BA_QRCHOL || variant == BA_CHOLESKY || qr_csne) {
       // QR variants: y = S^-1 g, dx_cam = -y. CHOLESKY: g already holds b_c - W V^-1 b_p up to sign (see k_schur), same sign rule.
       if (!solved_in_factor) {
         k_band_ldlt_solve<T><<<1, SOLVE_THREADS, 0, stream>>>(band(), d_dvec.p, gvec(), d_dx_cam.p, T(-1));
@@ -885,6 +904,31 @@ struct Impl : ba_handle {
     return BA_OK;
   }
 
+  // QRKIT / MOREQR: corrected semi-normal refinement of dx_cam = -y0 (see k_csne_point): r = J2bot^T (d - J2bot y0) through
+  // the D records, S delta = r with the kept copy of S, dx_cam -= delta
+  int csne_refine(T lamT) {
+    const T sl = (T)std::sqrt(lamT);
+    const T diag = sl * sl;
+    for (int it = 0; it < csne_steps; ++it) {
+      if (nunits) k_csne_point<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, 0, stream>>>(nunits, d_unit_pt.p, d_seg.p, d_slot.p, d_view.p, d_D.p, d_dx_cam.p, d_u.p);
+      if (nlong) k_csne_point_long<T><<<(nlong + TILE / 32 - 1) / (TILE / 32), TILE, 0, stream>>>(nlong, d_long_pt.p, d_pt_start.p, d_slot.p, d_view.p, d_D.p, d_dx_cam.p, d_u.p);
+      k_csne_cam<T><<<N, 128, 0, stream>>>(d_cam_start.p, d_D.p, d_u.p, d_dx_cam.p, rank == 0 ? diag : T(0), gvec());
+      launches += 2 + (nlong ? 1 : 0);
+      CK(cudaGetLastError());
+      if (comm) NK(g_nccl.AllReduce(gvec(), gvec(), (size_t)n, nccl_t(), ncclSum, comm, stream));
+      CK(cudaMemcpyAsync(d_red.p, d_keepS.p, red_count * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+      std::swap(d_dx_cam.p, d_delta.p);                 // the solvers write -S^-1 rhs into d_dx_cam
+      int rc = factor_reduced();
+      if (!rc) rc = solve_reduced();
+      std::swap(d_dx_cam.p, d_delta.p);
+      if (rc) return rc;
+      k_axpy1<T><<<std::max(1, std::min(64, (n + 255) / 256)), 256, 0, stream>>>(n, d_delta.p, d_dx_cam.p);
+      launches++;
+      CK(cudaGetLastError());
+    }
+    return BA_OK;
+  }
+
   int solve_try(double* dx_norm, double* rho_den, double* energy_test) override {
     CK(cudaSetDevice(device));
     if (!computed) return fail(BA_ERR_STATE, "ba_solve_try called before ba_compute");
@@ -892,6 +936,7 @@ struct Impl : ba_handle {
     mark(4);
     { int rc = solve_reduced(); if (rc) return rc; }
     CK(cudaGetLastError());
+    if (qr_csne) { int rc = csne_refine(lamT); if (rc) return rc; }
     mark(5);
     k_cam_update<T><<<1, 1024, 0, stream>>>(N, d_cams.p, d_dx_cam.p, gJvec(), d_cams_test.p, d_scal.p + 4, d_scal.p + 6);
     launches++;
@@ -1055,6 +1100,7 @@ struct Impl : ba_handle {
   int debug_band_solve(int n_, int kd_, const double* S, const double* g, double* yout) override {
     CK(cudaSetDevice(device));
     const int n0 = n, kd0 = kd, lds0 = ldsv; const size_t rc0 = red_count;
+    const bool csne0 = qr_csne; qr_csne = false;    // the hook exercises the Householder band QR itself for the QR variants
     n = n_; kd = std::max(1, std::min(kd_, n_ - 1)); ldsv = pad_lds(kd); red_count = (size_t)n * (ldsv + 1);
     DevBuf<T> red, yv, dv, dxc;
     CK(red.alloc(red_count + 2 * (size_t)n)); CK(yv.alloc(n)); CK(dv.alloc((size_t)n + NB)); CK(dxc.alloc(n));
@@ -1073,7 +1119,7 @@ struct Impl : ba_handle {
     }
     cudaStreamSynchronize(stream);
     std::swap(d_red.p, red.p); std::swap(d_dvec.p, dv.p); std::swap(d_dx_cam.p, dxc.p);
-    n = n0; kd = kd0; ldsv = lds0; red_count = rc0; d_qr.free();
+    n = n0; kd = kd0; ldsv = lds0; red_count = rc0; d_qr.free(); qr_csne = csne0;
     if (ce != cudaSuccess) return fail(BA_ERR_CUDA, "debug_band_solve upload: %s", cudaGetErrorString(ce));
     return rc;
   }

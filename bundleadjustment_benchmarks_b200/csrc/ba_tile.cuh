@@ -298,9 +298,10 @@ __device__ __forceinline__ void tile_phases_123(const TileArgs<T>& a, TileSmem<T
 //   P record, at the observation's index (point-major, so the back-substitution streams them):
 //             R12_i = Q1_i^T Jc_i, 3x9 row-major, one pad scalar       (off-diagonal blocks, back-substitution)
 //   D record, at the observation's CAMERA-MAJOR slot (observations sorted by (camera, point), so the diagonal
-//             kernel streams a camera's records): Jc_i 2x9 row-major | M_i = I2 - Q1_i Q1_i^T as m00 m01 m11 |
-//             w_i = e_i - Q1_i c | e_i | 3 pad
-//             (diagonal blocks: Jc^T Jc - R12^T R12 = Jc^T M Jc; g: Jc^T e - R12^T c = Jc^T w; gJ = Jc^T e)
+//             kernel streams a camera's records): Jc_i 2x9 row-major | Q1_i 2x3 (the observation's rows of the thin Q) |
+//             w_i = e_i - Q1_i c | e_i
+//             (diagonal blocks: Jc^T Jc - R12^T R12 = Jc^T M Jc with M_i = I2 - Q1_i Q1_i^T; g: Jc^T e - R12^T c = Jc^T w;
+//             gJ = Jc^T e; Q1_i also serves the corrected semi-normal refinement of the QR variants, k_csne_*)
 // and per point (R (6), c (3), G = Jp^T e (3), perm, pad) = 16 scalars.
 // Pass 2: k_schur_gather (one warp per off-diagonal block, one LANE per pair with the whole 9x9 block in
 // registers, records staged through shared memory with cp.async one batch of 32 pairs ahead) and
@@ -346,12 +347,10 @@ template <class T> __device__ __forceinline__ void store_rec(T* p, const T (&v)[
 template <class T>
 __device__ __forceinline__ void fill_drec_tail(T (&rec)[REC], const T q00, const T q01, const T q02, const T q10, const T q11, const T q12,
                                                const T c0, const T c1, const T c2, const T e0, const T e1) {
-  rec[18] = T(1) - (q00 * q00 + q01 * q01 + q02 * q02);
-  rec[19] = -(q00 * q10 + q01 * q11 + q02 * q12);
-  rec[20] = T(1) - (q10 * q10 + q11 * q11 + q12 * q12);
-  rec[21] = e0 - (q00 * c0 + q01 * c1 + q02 * c2);
-  rec[22] = e1 - (q10 * c0 + q11 * c1 + q12 * c2);
-  rec[23] = e0; rec[24] = e1; rec[25] = T(0); rec[26] = T(0); rec[27] = T(0);
+  rec[18] = q00; rec[19] = q01; rec[20] = q02; rec[21] = q10; rec[22] = q11; rec[23] = q12;
+  rec[24] = e0 - (q00 * c0 + q01 * c1 + q02 * c2);
+  rec[25] = e1 - (q10 * c0 + q11 * c1 + q12 * c2);
+  rec[26] = e0; rec[27] = e1;
 }
 
 template <class T>
@@ -893,7 +892,11 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) k_schur_diag(const int* __res
     if (lane < cnt) {
       T r[REC];
       lds_rec<0, REC>(wbuf + ((size_t)st * 32 + lane) * SR, r);
-      const T m00 = r[18], m01 = r[19], m11 = r[20], w0 = r[21], w1 = r[22], e0 = r[23], e1 = r[24];
+      // M_i = I2 - Q1_i Q1_i^T from the observation's thin-Q rows
+      const T m00 = T(1) - (r[18] * r[18] + r[19] * r[19] + r[20] * r[20]);
+      const T m01 = -(r[18] * r[21] + r[19] * r[22] + r[20] * r[23]);
+      const T m11 = T(1) - (r[21] * r[21] + r[22] * r[22] + r[23] * r[23]);
+      const T w0 = r[24], w1 = r[25], e0 = r[26], e1 = r[27];
       T t0[9], t1[9];
 #pragma unroll
       for (int b = 0; b < 9; ++b) {
@@ -1258,6 +1261,128 @@ __global__ void __launch_bounds__(TILE, 4) k_moreqr_stage2(const T lambda, int n
     store4(q + 8, cq[2], G[0], G[1], G[2]);
     store4(q + 12, (T)pm, T(0), T(0), T(0));
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Right block of QRKIT / MOREQR (DenseBlockedThinQR of J2bot, BAFunctor.h:101,111; call sites More.h:288,328). The tall
+// J2bot ((2K+9N) x 9N dense: 1.3 TB at BASELINE config 5) cannot be materialised, and a Householder QR of the SQUARE
+// S = J2bot^T J2bot has the accuracy of the normal equations at 4-10x the cost of an LDL^T. What a QR of J2bot buys is a
+// solution whose error does not carry cond(S) = cond(J2bot)^2 from FORMING S; the same is obtained with the corrected
+// semi-normal equations (Bjorck 1987): y0 from the factor of S, then the residual of the LEAST-SQUARES problem taken
+// through J2bot itself, never through S,
+//     rho = d - J2bot y0,   J2bot^T rho = sum_i Jc_i^T u_i - lambda y0,   u = (I - Q1 Q1^T)(e - Jc y0)  (per point),
+// one more solve S delta = J2bot^T rho, y = y0 + delta. J2bot is never formed: Jc_i, Q1_i, e_i sit in the D records.
+//   k_csne_point (point-major, warp units, lane = observation; k_csne_point_long: one warp per point with more than 32
+//   observations): u_i into the observation's camera-major slot;  k_csne_cam (one CTA per camera, fixed-order sums):
+//   r_a = sum Jc_i^T u_i + lambda dx_cam_a  (dx_cam = -y0).
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void csne_load(const T* __restrict__ Drec, const size_t sl, const T* __restrict__ dx_cam, const int cam, T (&q)[2][3], T& et0, T& et1) {
+  T r[REC];
+#pragma unroll
+  for (int c = 0; c < REC; c += 4) load4(Drec + sl * REC + c, r[c], r[c + 1], r[c + 2], r[c + 3]);
+  et0 = r[26]; et1 = r[27];
+#pragma unroll
+  for (int b = 0; b < 9; ++b) { const T d = __ldg(dx_cam + 9 * (size_t)cam + b); et0 += r[b] * d; et1 += r[9 + b] * d; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { q[0][k] = r[18 + k]; q[1][k] = r[21 + k]; }
+}
+
+template <class T>
+__global__ void __launch_bounds__(TILE) k_csne_point(int nunits, const int* __restrict__ unit_obs, const int* __restrict__ seg, const int* __restrict__ slot,
+                                                     const int* __restrict__ view, const T* __restrict__ Drec, const T* __restrict__ dx_cam, T* __restrict__ uarr) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, u = blockIdx.x * (TILE / 32) + (threadIdx.x >> 5);
+  if (u >= nunits) return;
+  const int2 uo = __ldg(reinterpret_cast<const int2*>(unit_obs) + u);
+  const int o0 = uo.x, un = uo.y;
+  const bool act = lane < un;
+  const int o = o0 + (act ? lane : 0);
+  const int cam = __ldg(view + o), sg = __ldg(seg + o);
+  const size_t sl = (size_t)__ldg(slot + o);
+  const int i = act ? (sg & 0xff) : 0, n = act ? (sg >> 8) : 1;
+  const int s0 = lane - i;
+  T q[2][3], et0, et1;
+  csne_load<T>(Drec, sl, dx_cam, cam, q, et0, et1);
+  if (!act) { et0 = et1 = T(0); }
+  const int nmax = __reduce_max_sync(FULL, n);
+  T t[3] = {q[0][0] * et0 + q[1][0] * et1, q[0][1] * et0 + q[1][1] * et1, q[0][2] * et0 + q[1][2] * et1};
+  seg_sum<T, 3>(t, s0, n, nmax, i);
+  if (act) {
+    uarr[2 * sl] = et0 - (q[0][0] * t[0] + q[0][1] * t[1] + q[0][2] * t[2]);
+    uarr[2 * sl + 1] = et1 - (q[1][0] * t[0] + q[1][1] * t[1] + q[1][2] * t[2]);
+  }
+}
+
+// points with more than 32 observations: one warp per point, two sweeps over its observations (fixed order)
+template <class T>
+__global__ void __launch_bounds__(TILE) k_csne_point_long(int nlong, const int* __restrict__ long_pt, const int* __restrict__ pt_start, const int* __restrict__ slot,
+                                                          const int* __restrict__ view, const T* __restrict__ Drec, const T* __restrict__ dx_cam, T* __restrict__ uarr) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = blockIdx.x * (TILE / 32) + (threadIdx.x >> 5);
+  if (w >= nlong) return;
+  const int pj = __ldg(long_pt + w), o0 = __ldg(pt_start + pj), n = __ldg(pt_start + pj + 1) - o0;
+  T t[3] = {T(0), T(0), T(0)};
+  for (int base = 0; base < n; base += 32) {
+    const int ii = base + lane;
+    T c3[3] = {T(0), T(0), T(0)};
+    if (ii < n) {
+      T q[2][3], et0, et1;
+      csne_load<T>(Drec, (size_t)__ldg(slot + o0 + ii), dx_cam, __ldg(view + o0 + ii), q, et0, et1);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) c3[k] = q[0][k] * et0 + q[1][k] * et1;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) c3[k] += __shfl_down_sync(FULL, c3[k], off);
+      t[k] += __shfl_sync(FULL, c3[k], 0);
+    }
+  }
+  for (int base = 0; base < n; base += 32) {
+    const int ii = base + lane;
+    if (ii < n) {
+      T q[2][3], et0, et1;
+      const size_t sl = (size_t)__ldg(slot + o0 + ii);
+      csne_load<T>(Drec, sl, dx_cam, __ldg(view + o0 + ii), q, et0, et1);
+      uarr[2 * sl] = et0 - (q[0][0] * t[0] + q[0][1] * t[1] + q[0][2] * t[2]);
+      uarr[2 * sl + 1] = et1 - (q[1][0] * t[0] + q[1][1] * t[1] + q[1][2] * t[2]);
+    }
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(128) k_csne_cam(const int* __restrict__ cam_start, const T* __restrict__ Drec, const T* __restrict__ uarr,
+                                                  const T* __restrict__ dx_cam, const T lambda_diag, T* __restrict__ rout /* 9 per camera */) {
+  __shared__ T part[4][9];
+  const int cam = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T s[9];
+#pragma unroll
+  for (int b = 0; b < 9; ++b) s[b] = T(0);
+  for (int q = __ldg(cam_start + cam) + threadIdx.x; q < __ldg(cam_start + cam + 1); q += 128) {
+    const T* rec = Drec + (size_t)q * REC;
+    T jc[20];
+#pragma unroll
+    for (int c = 0; c < 20; c += 4) load4(rec + c, jc[c], jc[c + 1], jc[c + 2], jc[c + 3]);
+    const T u0 = __ldg(uarr + 2 * (size_t)q), u1 = __ldg(uarr + 2 * (size_t)q + 1);
+#pragma unroll
+    for (int b = 0; b < 9; ++b) s[b] += jc[b] * u0 + jc[9 + b] * u1;
+  }
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s[b] += __shfl_down_sync(0xffffffffu, s[b], off);
+    if (lane == 0) part[warp][b] = s[b];
+  }
+  __syncthreads();
+  if (threadIdx.x < 9)
+    rout[9 * (size_t)cam + threadIdx.x] = (((part[0][threadIdx.x] + part[1][threadIdx.x]) + part[2][threadIdx.x]) + part[3][threadIdx.x]) + lambda_diag * dx_cam[9 * (size_t)cam + threadIdx.x];
+}
+
+// dx_cam += delta
+template <class T>
+__global__ void k_axpy1(int n, const T* __restrict__ x, T* __restrict__ y) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += x[i];
 }
 
 // ---------------------------------------------------------------------------------------------

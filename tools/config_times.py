@@ -2,8 +2,11 @@
 import sys; sys.path.insert(0, ".")
 import numpy as np
 from bundleadjustment_benchmarks_b200 import bal, solver
-for name, variants in (("problem-16-22106", ("QRKIT",)), ("problem-21-11315", ("CHOLESKY",)), ("problem-39-18060", ("QRCHOL", "MOREQR")),
-                       ("problem-126-40037", ("QRCHOL", "MOREQR")), ("problem-257-65132", ("QRKIT", "QRCHOL"))):
+cfgs = [("problem-16-22106", ("QRKIT",)), ("problem-21-11315", ("CHOLESKY",)), ("problem-39-18060", ("QRCHOL", "MOREQR")),
+        ("problem-126-40037", ("QRCHOL", "MOREQR")), ("problem-257-65132", ("QRKIT", "QRCHOL"))]
+if len(sys.argv) > 1 and sys.argv[1] == "all":
+    cfgs.append(("synthetic-5m", ("QRCHOL", "QRKIT", "MOREQR", "CHOLESKY")))
+for name, variants in cfgs:
     p = bal.load_named(name)
     for v in variants:
         s = solver.GpuSolver(p, v)
