@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--precision", default="f64", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-probe", action="store_true")
+    ap.add_argument("--no-other-variant", action="store_true")
     return ap.parse_args()
 
 
@@ -70,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
         except OSError:
             self.proc = None
             return
@@ -79,9 +80,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append([t.strip() for t in line.split(",")])
+            self.samples.append((time.perf_counter(), [t.strip() for t in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        t0 = time.perf_counter()
+        while not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock and throttle reasons of the samples taken inside [t_begin, t_end] (the timed regions)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -90,7 +97,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for s in self.samples:
+        inside = [v for (t, v) in self.samples if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.05)]
+        for s in (inside or [v for (_, v) in self.samples]):
             try:
                 sm.append(float(s[0])); mx.append(float(s[1]))
             except (ValueError, IndexError):
@@ -99,7 +107,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_regions": len(inside)}
 
 
 # --------------------------------------------------------------------------------- CPU oracle legs
@@ -258,21 +266,22 @@ def run_ours(args):
         s.reject()
         return out
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    # ---- device-timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # ---- device-timed region
     l0 = s.launches()
     barrier()
+    t_region0 = time.perf_counter()
     s.timer_start()
     for _ in range(args.steps):
         dxn, rho_den, et = step()
     dev_ms = s.timer_stop()
     barrier()
     launches = s.launches() - l0
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = max_over_ranks(dev_ms) / args.steps
 
     # ---- end-to-end region: PINNED host buffers through the C ABI every step (state upload + step download)
@@ -300,6 +309,7 @@ def run_ours(args):
         e2e_step()
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    clocks = sampler.stop(t_region0, time.perf_counter()) if rank == 0 else None
 
     # ---- per-stage device times (CUDA events on the library stream) for the roofline of the dominant kernel
     s.set_profiling(True)
@@ -342,15 +352,15 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get(f"{args.workload}:{args.variant}:{args.precision}", {}).get(dom)
         except Exception:
             traffic = None
-    kernel_name = {"factor": "k_band_ldlt_cluster" if args.variant in ("QRCHOL", "CHOLESKY") else "k_band_qr",
-                   "reduced_solve": "k_band_ldlt_cluster (solve folded in)" if args.variant in ("QRCHOL", "CHOLESKY") else "k_band_qr_backsolve",
+    kernel_name = {"factor": "k_band_ldlt_cluster",
+                   "reduced_solve": "k_band_ldlt_cluster (solve folded in)" if args.variant in ("QRCHOL", "CHOLESKY") else "k_csne_point + k_csne_cam + k_band_ldlt_cluster (refinement solve)",
                    "k_schur_gather": "k_schur_diag + k_schur_gather"}.get(dom, dom)
     n_red = 9 * N
     if dom == "factor":
         # the band factorisation is an FP64 contraction (n kd^2 flops for LDL^T, 4x for Householder QR of the
         # square band) on the FP64 tensor pipe (DMMA); peak = 64 FMA/clk/SM measured with tools/ubench
         # (DMMA m8n8k4 and DFMA both) x 148 SMs x max SM clock
-        flops = float(n_red) * kd * kd * (1.0 if args.variant in ("QRCHOL", "CHOLESKY") else 4.0)
+        flops = float(n_red) * kd * kd   # LDL^T of the band (all variants: the QR variants refine its solution through J2bot)
         fpath = os.path.join(ROOT, "profiles", "fp64_peak.json")
         if os.path.exists(fpath):
             fp = json.load(open(fpath))
@@ -422,6 +432,44 @@ def run_ours(args):
             if not probe["ok"]:
                 raise SystemExit(f"parity probe failed at {world} rank(s): {probe}")
 
+    # ---- the other variant BASELINE config 5 names (QRKIT next to the QRCHOL headline, or vice versa): same step, device time
+    other = None
+    if args.workload == "synthetic-5m" and args.variant in ("QRCHOL", "QRKIT") and not args.no_other_variant:
+        ov = "QRKIT" if args.variant == "QRCHOL" else "QRCHOL"
+        s2 = solver.GpuSolver(prob, ov, args.precision, device=local_rank)
+        if world > 1:
+            uid3 = [None]
+            if rank == 0:
+                buf3 = C.create_string_buffer(128)
+                assert _lib.lib().ba_comm_unique_id(buf3) == 0, _lib.lib().ba_last_error()
+                uid3[0] = buf3.raw
+            dist.broadcast_object_list(uid3, src=0)
+            s2.set_bandwidth(sharding.global_bandwidth(full))
+            s2.comm_init(rank, world, uid3[0])
+        s2.linearize(colnorms=True)
+
+        def step2():
+            s2.linearize(colnorms=False)
+            s2.compute(lam)
+            out = s2.solve_try()
+            s2.reject()
+            return out
+
+        for _ in range(3):
+            step2()
+        nst = max(3, min(args.steps, 10))
+        barrier()
+        s2.timer_start()
+        for _ in range(nst):
+            step2()
+        ms2 = max_over_ranks(s2.timer_stop()) / nst
+        barrier()
+        s2.set_profiling(True)
+        step2()
+        st2 = s2.stage_ms()
+        other = {"variant": ov, "ms_per_step": ms2, "steps": nst, "stages_ms": {n_: float(v) for n_, v in zip(names, st2)}}
+        s2.close()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only (the scaling runs carry null)
         cpu_baseline = cpu_baseline_legs(full, args.variant)
@@ -434,7 +482,8 @@ def run_ours(args):
                 "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "check": {"energy": e0, "energy_test": et, "dx_norm": dxn, "lambda": lam}, "parity_probe": probe}
+                "check": {"energy": e0, "energy_test": et, "dx_norm": dxn, "lambda": lam}, "parity_probe": probe,
+                "variants": other}
         print(json.dumps(line), flush=True)
     s.close()
     if world > 1:
