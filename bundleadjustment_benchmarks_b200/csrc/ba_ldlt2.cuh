@@ -27,7 +27,7 @@ namespace ba {
 constexpr int L2_MAX_BT = 18;        // row tiles below the diagonal a panel may touch (kd <= 576)
 constexpr int L2_NSLOT = 15;         // resident C tiles per CTA (bt = 18: 5 + 4 + 3 + 2 + 1 over the five diagonals = r - c mod 4)
 constexpr int L2_NOP = 5;            // operand tiles per role per CTA
-constexpr int L2_UW = 6;             // update warps per CTA: 1, 2, 3, 5, 6, 7 (warps 0 and 4 share SMSP 0 and run the chain)
+constexpr int L2_UW = 5;             // update warps of the CTA that runs the chain: 1, 2, 3, 6, 7
 constexpr int L2_UT = 32 * L2_UW;
 constexpr int L2_TILE = NB * NB;
 
@@ -43,6 +43,7 @@ struct Ldlt2Smem {
   int snb[8];                                    // slots of that class
   long long tc[16];                              // phase cycle counters (-DBA_L2_TICKS)
   int chain_done;                                // this CTA's chain warp published panel p: p + 1 (warp 0 -> warp 4)
+  int col_ready;                                 // the owner of this CTA's helper column has finished its column tiles of panel p: p + 1 (written remotely by that owner)
   int prio_cnt;                                  // column tiles that have received their last update (running count, all panels)
   int panel_ready;                               // W_p, D_p, z_p of panel p are in global memory: p + 1 (written by the diagonal owner's warp 4 into the four CTAs that own column p)
 };
@@ -51,9 +52,10 @@ struct Ldlt2Smem {
 __device__ __forceinline__ int l2_swz(int r, int c) { return r * NB + ((((c >> 1) ^ ((r & 3) << 1)) << 1) | (c & 1)); }
 __device__ __forceinline__ void l2_st_release_cluster(int* p, int v) { asm volatile("st.release.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ int l2_ld_acquire_cluster(const int* p) { int v; asm volatile("ld.acquire.cluster.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void l2_red_release_cta(int* p, int v) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-  asm volatile("red.release.cta.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+__device__ __forceinline__ int l2_atom_add_acq_rel_cta(int* p, int v) {
+  int old; const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("atom.acq_rel.cta.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
 }
 __device__ __forceinline__ void l2_bar_update(const int nthr) { asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); }
 
@@ -292,7 +294,7 @@ __device__ __forceinline__ void l2_warp_w32(double (&a)[NB], const PanelSmem<dou
 #ifndef BA_L2_EVK
 #define BA_L2_EVK 101
 #endif
-#define L2EV(e) { if (dbg && lane == 0 && k == BA_L2_EVK && blockIdx.x < 16 && (warp == 0 || warp == 1 || warp == 4)) dbg[16 + rank * 12 + (warp == 0 ? 0 : warp == 1 ? 4 : 8) + (e)] = clock64() - tev0; }
+#define L2EV(e) { if (dbg && lane == 0 && k == BA_L2_EVK && blockIdx.x < 16 && (warp == 0 || warp == 1 || warp == 5)) dbg[16 + rank * 12 + (warp == 0 ? 0 : warp == 1 ? 4 : 8) + (e)] = clock64() - tev0; }
 #else
 #define L2TICK(i) {}
 #define L2EV(e) {}
@@ -308,8 +310,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
   Ldlt2Smem& sm = *reinterpret_cast<Ldlt2Smem*>(l2_smem_raw);
   const int rank = (int)cluster.block_rank(), r = rank >> 2, c = rank & 3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool upd_warp = (warp & 3) != 0;
-  const int u = (warp < 4) ? warp - 1 : warp - 2;      // 0..5 over warps 1, 2, 3, 5, 6, 7
+  // In the CTA that runs the chain: warp 0 factors and has SMSP 0 to itself (warp 4 idles: the W-forming warp next to it
+  // on the same SMSP made the factorisation take 4.9 us instead of ~3), warp 5 forms W_k, warps 1, 2, 3, 6, 7 update.
+  const bool upd_warp = (warp & 3) != 0 && warp != 5;
+  const int u = (warp < 4) ? warp - 1 : warp - 3;      // 0..4 over warps 1, 2, 3, 6, 7
   const int ut = u * 32 + lane;                         // thread index among the update warps
   const int n = A.n, kd = A.kd, lds = (int)A.lds;
   const int nt = (n + NB - 1) / NB, bt = (kd + NB - 1) / NB;
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
   if (tid < 2 * NB) { sm.pn.sCol[0][NB + (tid & 31)] = 0.0; sm.pn.sCol[1][NB + (tid & 31)] = 0.0; }
   if (tid < 16) sm.tc[tid] = 0;
   if (tid == 0) {
-    sm.pn.progress = 0; sm.chain_done = 0; sm.panel_ready = 0; sm.prio_cnt = 0;
+    sm.pn.progress = 0; sm.chain_done = 0; sm.panel_ready = 0; sm.prio_cnt = 0; sm.col_ready = 0;
     const int d0 = (r - c + 4) & 3;
     int b = 0;
     for (int dq = 0; dq < 8; ++dq) {
@@ -335,6 +339,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
     return sm.slot[sm.sbase[dq] + ((j >> 2) % sm.snb[dq])];
   };
   auto diag_owner = [](const int k) { return 5 * (k & 3); };
+  // The chain of panel k+1 (iteration k) does NOT run on the owner of the diagonal tile: that CTA, like every owner of
+  // column k+1, is at the peak of its load in iteration k (its first column is k+1: 15 tiles for the classes r - c = 0, 1).
+  // It runs on the CTA whose first column is k+4, class r - c = 3: six tiles at bt = 18, the lightest of the cluster, which
+  // also leaves slots 13 and 14 of that CTA free: the diagonal tile is pushed there through distributed shared memory by
+  // its owner when it receives panel k-1's update, the operand L(k+1, k) is staged into slot 13.
+  auto chain_cta = [](const int k) { return 4 * ((k + 3) & 3) + (k & 3); };
+  constexpr int SLOT_DIAG = L2_NSLOT - 1, SLOT_OPND = L2_NSLOT - 2;
 
   // ---- factorisation of the diagonal tile of panel k by warp 0 (registers a[] = rows, z = right-hand side), publication
   auto factor_publish = [&](double (&a)[NB], const double z, const int k) {
@@ -362,7 +373,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
     // W_k is out; once the chain warp has published D_k, z_k and the diagonal tile too, tell the owners of column k
     if (lane < 4) {
       while (ld_acquire_cta(&sm.chain_done) < k + 1) {}
-      l2_st_release_cluster(cluster.map_shared_rank(&sm.panel_ready, 4 * lane + (k & 3)), k + 1);
+      l2_st_release_cluster(cluster.map_shared_rank(&sm.panel_ready, 4 * lane + (k == 0 ? 0 : ((k - 1) & 3))), k + 1);
     }
     __syncwarp();
   };
@@ -372,41 +383,50 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
   // q = (row tile q / 2, half q % 2) goes to participating warp q % nw; the row operand comes straight from the tile's
   // slot (accumulator order, read in fragment order), W_k / D_k / z_k straight from L2, the result straight to the band
   // storage: no shared scratch, no CTA barrier, so the rest of the window update goes on around it.
-  auto solve_column = [&](const int k, const int wi, const int nw, const int prio_target) {
+  // slot of tile (i, j) in a CTA of diagonal class d0c (the table in shared memory is this CTA's own class)
+  auto slot_index_cls = [&](const int d0c, const int i, const int j) -> int {
+    const int dq = (i - j) >> 2;
+    int b = 0;
+    for (int q = 0; q < dq; ++q) { const int d = d0c + 4 * q; b += (d < bt) ? (bt - d + 3) / 4 : 0; }
+    const int nb = (bt - (d0c + 4 * dq) + 3) / 4;
+    return b + ((j >> 2) % nb);
+  };
+  auto solve_column = [&](const int k, const int wi, const int nw, const int owner, const bool wait_col) {
     const int k0 = k * NB, hi = min(k + bt, nt - 1);
     const int ia0 = (k + 1) + ((r - (k + 1)) & 3);
     const int ntile = (hi >= ia0) ? ((hi - ia0) >> 2) + 1 : 0;
     if (wi >= 2 * ntile) return;
     if (lane == 0) {
       while (l2_ld_acquire_cluster(&sm.panel_ready) < k + 1) {}
-      while (ld_acquire_cta(&sm.prio_cnt) < prio_target) {}
+      if (wait_col) { while (l2_ld_acquire_cluster(&sm.col_ready) < k + 1) {} }
     }
     __syncwarp();
     (void)l2_ld_acquire_cluster(&sm.panel_ready);
-    (void)ld_acquire_cta(&sm.prio_cnt);
+    if (wait_col) (void)l2_ld_acquire_cluster(&sm.col_ready);
+    const int d0o = (r - (k & 3)) & 3;                              // class of the column's owner (r, k mod 4)
     const int lr = lane >> 2, lc = lane & 3;
     const double* Wk = Wbuf + (size_t)k * NB * NB;
+    // column operands, once per warp: W_k (lower triangular), 1 / D_k and z_k of this lane's eight columns
+    double bf[4][NB / 4], invd[8], zk[8];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int kk = 0; kk < NB / 4; ++kk) bf[ni][kk] = (kk <= 2 * ni + 1) ? Wk[(ni * 8 + lr) * NB + kk * 4 + lc] : 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = (e >> 1) * 8 + 2 * lc + (e & 1);
+      invd[e] = pivot_rcp(dvec[k0 + col]);
+      zk[e] = *((k0 + col < n) ? zscr + k0 + col : zp);
+    }
     for (int q = wi; q < 2 * ntile; q += nw) {
       const int t = q >> 1, h = q & 1, i = ia0 + 4 * t;
-      // column operands: W_k (lower triangular), 1 / D_k and z_k of this lane's eight columns
-      double bf[4][NB / 4], invd[8], zk[8];
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-        for (int kk = 0; kk < NB / 4; ++kk) bf[ni][kk] = (kk <= 2 * ni + 1) ? Wk[(ni * 8 + lr) * NB + kk * 4 + lc] : 0.0;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int col = (e >> 1) * 8 + 2 * lc + (e & 1);
-        invd[e] = dvec[k0 + col];
-        zk[e] = *((k0 + col < n) ? zscr + k0 + col : zp);
-      }
       double rold[2];
 #pragma unroll
       for (int ml = 0; ml < 2; ++ml) { const int gi = i * NB + (2 * h + ml) * 8 + lr; rold[ml] = *((lc == 0 && gi < n) ? rhs + gi : zp); }
       // row operand in fragment order: A(8 (2h + ml) + lr, 4 kk + lc)
       double af[2][NB / 4];
-      if (k > max(0, i - bt)) {                                   // received at least one update: lives in its slot
-        const double* sl = slot_of(i, k);
+      if (k > max(0, i - bt)) {                                   // received at least one update: lives in its owner's slot
+        const double* sl = (owner < 0) ? slot_of(i, k) : cluster.map_shared_rank(&sm.slot[slot_index_cls(d0o, i, k)][0], owner);
 #pragma unroll
         for (int ml = 0; ml < 2; ++ml)
 #pragma unroll
@@ -439,7 +459,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int ce = ((e >> 1) & 3) * 2 + (e & 1);                // index into this lane's eight columns
-        x[e] *= pivot_rcp(invd[ce]);
+        x[e] *= invd[ce];
         part[e >> 3] += x[e] * zk[ce];
       }
 #pragma unroll
@@ -480,11 +500,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
       }
       const double z = *((gi < n) ? rhs + gi : zp);
       factor_publish(a, z, 0);
-    } else if (warp == 4) {
+    } else if (warp == 5) {
       form_w(0);
     }
   }
-  if (np_fwd > 0 && c == 0) solve_column(0, warp, CL_WARPS, 0);
+  if (np_fwd > 0 && c == 0) solve_column(0, warp, CL_WARPS, -1, false);
   cluster.sync();
 
   int prio_target = 0;   // running number of column tiles this CTA has to finish before it may solve the column (same on every warp)
@@ -498,11 +518,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
     // ======================= U(k): the window receives panel k's update; F(k+1) on the owner of the next diagonal tile
     const bool prio = (k + 1 < np_fwd);                 // the tile (k+1, k+1) goes to the chain warp
     const bool last = (k == np_fwd - 1);                // last panel: updated tiles also return to the band storage
-    const bool chain_here = prio && rank == diag_owner(k + 1);   // warps 0 and 4 of this CTA run the chain of panel k+1
+    const bool chain_here = prio && rank == chain_cta(k);        // warps 0 and 4 of this CTA run the chain of panel k+1
     const int nuw = chain_here ? L2_UW : CL_WARPS;               // otherwise they update like everybody else
     const int uw = chain_here ? (upd_warp ? u : -1) : warp;
-    const bool col_cta = prio && c == ((k + 1) & 3);             // this CTA owns tiles of column k+1: it solves them (T(k+1))
-    if (col_cta) { for (int i = (k + 2) + ((r - (k + 2)) & 3); i <= hi; i += 4) ++prio_target; }
+    // Column k+1: its owners (column class (k+1) mod 4, at the peak of their load) only finish its tiles; the solves T(k+1)
+    // run on their row neighbours with column class k mod 4 (first column k+4: the lightest CTAs), which read the tiles
+    // from the owner's slots through distributed shared memory once the owner's flag is up.
+    const bool col_cta = prio && c == ((k + 1) & 3);
+    const bool hlp_cta = prio && c == (k & 3);
+    int ncol = 0;                                                 // column tiles of row class r that receive panel k's update
+    if (prio) { for (int i = (k + 2) + ((r - (k + 2)) & 3); i <= hi; i += 4) ++ncol; }
+    if (col_cta) prio_target += ncol;
     if (uw >= 0) {
       const int nthr = 32 * nuw, utx = 32 * uw + lane;
       for (int t = 0, i = ia0; i <= hi; ++t, i += 4) {
@@ -512,6 +538,16 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
       for (int t = 0, j = jb0; j <= hi; ++t, j += 4) l2_stage_tile(sm.opB[t], A, j, k0, utx, nthr);
       cp_async_commit();
       if (utx < NB) sm.sdU[utx] = dvec[k0 + utx];
+      // the tiles of the row that enters the window (first update from panel k) come from the band storage into their
+      // slots while the operands are in flight
+      if (k >= 1) {
+        const int ie = k + bt;
+        if (ie <= nt - 1 && ((ie - r) & 3) == 0) {
+          int tt = 0;
+          for (int j = jb0; j <= ie; j += 4, ++tt)
+            if (tt % nuw == uw && !(prio && ie == k + 1 && j == k + 1)) { double acc[32]; l2_load_tile(A, ie, j, lane, acc); l2_store_slot(slot_of(ie, j), lane, acc); }
+        }
+      }
       cp_async_wait_all();
       for (int t = 0, i = ia0; i <= hi; ++t, i += 4) {
         if (prio && i == k + 1) continue;
@@ -526,51 +562,59 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
       for (int kk = 0; kk < NB / 4; ++kk) ms[kk] = -sm.sdU[kk * 4 + (lane & 3)];
       // Column k+1 comes first (jb0 = k+1 on its owners); every such tile bumps prio_cnt when its update is stored, and a
       // warp solves its share of the column (T(k+1)) as soon as the chain's flag is up, between two tile updates.
-      bool t_pending = col_cta;
+      bool t_pending = hlp_cta;
+      const int owner = 4 * r + ((k + 1) & 3);
       int t = 0;
       for (int jt = 0, j = jb0; j <= hi; ++jt, j += 4) {
         const int i0 = j + ((r - j) & 3);
         for (int i = i0; i <= hi; i += 4) {
           if (prio && i == k + 1 && j == k + 1) continue;
-          if (t_pending && j > k + 1 && l2_ld_acquire_cluster(&sm.panel_ready) >= k + 2 && ld_acquire_cta(&sm.prio_cnt) >= prio_target) {
-            solve_column(k + 1, uw, nuw, prio_target);
+          if (t_pending && l2_ld_acquire_cluster(&sm.panel_ready) >= k + 2 && (ncol == 0 || l2_ld_acquire_cluster(&sm.col_ready) >= k + 2)) {
+            solve_column(k + 1, uw, nuw, owner, ncol > 0);
             t_pending = false;
           }
           if (t % nuw == uw) {
             double acc[32];
             double* s = slot_of(i, j);
-            const bool first = (k == max(0, i - bt));
+            const bool first = (k == 0);
             if (first) l2_load_tile(A, i, j, lane, acc); else l2_load_slot(s, lane, acc);
             if (i == j) l2_mma<1>(sm.opA[(i - ia0) >> 2], sm.opB[jt], ms, lane, acc);
             else l2_mma<0>(sm.opA[(i - ia0) >> 2], sm.opB[jt], ms, lane, acc);
             if (last) l2_store_tile(A, i, j, lane, acc); else l2_store_slot(s, lane, acc);
-            if (col_cta && j == k + 1) { __syncwarp(); if (lane == 0) l2_red_release_cta(&sm.prio_cnt, 1); }
+            if (i == k + 2 && j == k + 2 && k + 2 < np_fwd)          // next iteration's chain works on it: hand it over
+              l2_store_slot(cluster.map_shared_rank(&sm.slot[SLOT_DIAG][0], chain_cta(k + 1)), lane, acc);
+            if (col_cta && j == k + 1) {                               // the last one tells the helper CTA
+              __syncwarp();
+              if (lane == 0 && l2_atom_add_acq_rel_cta(&sm.prio_cnt, 1) + 1 == prio_target)
+                l2_st_release_cluster(cluster.map_shared_rank(&sm.col_ready, 4 * r + (k & 3)), k + 2);
+            }
           }
           ++t;
         }
       }
       if (warp == 1) L2TICK(7)
       L2EV(1)
-      if (t_pending) solve_column(k + 1, uw, nuw, prio_target);
+      if (t_pending) solve_column(k + 1, uw, nuw, owner, ncol > 0);
       L2EV(2)
       if (warp == 1) L2TICK(5)
     } else {   // chain_here: warps 0 and 4
       const int k1 = k + 1;
       if (warp == 0) {
-        l2_stage_tile(sm.opA[0], A, k1, k0, lane, 32);  // L(k+1, k): both operands of the diagonal update
+        double* const opnd = &sm.slot[SLOT_OPND][0];
+        l2_stage_tile(opnd, A, k1, k0, lane, 32);       // L(k+1, k): both operands of the diagonal update
         cp_async_commit();
         double acc[32], ms[NB / 4];
-        if (k == max(0, k1 - bt)) l2_load_tile(A, k1, k1, lane, acc); else l2_load_slot(slot_of(k1, k1), lane, acc);
+        if (k == max(0, k1 - bt)) l2_load_tile(A, k1, k1, lane, acc); else l2_load_slot(&sm.slot[SLOT_DIAG][0], lane, acc);
 #pragma unroll
         for (int kk = 0; kk < NB / 4; ++kk) ms[kk] = -dvec[k0 + kk * 4 + (lane & 3)];
         const int gi = k1 * NB + lane;
         const double z = *((gi < n) ? rhs + gi : zp);
         cp_async_wait_all();
-        l2_fix_tile(sm.opA[0], A, k1, k0, lane, 32);
+        l2_fix_tile(opnd, A, k1, k0, lane, 32);
         __syncwarp();
         L2TICK(0)
         L2EV(0)
-        l2_mma<1>(sm.opA[0], sm.opA[0], ms, lane, acc);
+        l2_mma<1>(opnd, opnd, ms, lane, acc);
         L2TICK(1)
         // accumulator order -> one row per lane through the (idle) L_kk^T buffer, rows rotated by their index
         double* stg = &sm.pn.sLT[0][0];
@@ -596,7 +640,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_fwd2(const LdltJob<
         factor_publish(a, z, k1);
         L2TICK(3)
         L2EV(2)
-      } else {  // warp 4
+      } else if (warp == 5) {
         form_w(k1);
         L2EV(0)
       }
