@@ -987,13 +987,20 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
   // ------------------------------------------------------------------ backward pass, whole cluster
   T* slots = &sm.gA[0][0][0][0][0];                    // [2][bt][NB] far-tile partial sums, written through DSMEM
   T* slots0 = cluster.map_shared_rank(slots, 0);    // CTA 0's copy
+  // y_k of the blocks solved in this launch lives in a ring in CTA 0's shared memory (read by the other CTAs through
+  // DSMEM); it is written to global memory one step later by another warp, so that no cluster barrier ever waits for
+  // the round trip of a global store (measured: 0.72 us of the 1.9 us per step)
+  constexpr int RB = 256;                           // ring blocks (>= CL_MAX_BT + 2), in the idle column-operand area
+  static_assert(RB * NB <= 2 * 2 * CL_GROUPS * NB * TS && RB >= CL_MAX_BT + 2, "y ring must fit the staging area");
+  T* ring = &sm.gB[0][0][0][0][0];
+  const T* ring0 = cluster.map_shared_rank(ring, 0);
   auto stage = [&](int km) {  // everything step km needs except y_{km+1}: executed one step ahead
     const int km0 = km * NB;
     const int nfar = min(nt - 1, km + bt) - (km + 2) + 1;
     if (warp >= 1 && warp <= 3) {
       for (int s = rank + C * (warp - 1); s < nfar; s += C * 3) {
         const int i = km + 2 + s, gj = km0 + lane;
-        const T yv = *((i * NB + lane < n) ? y + i * NB + lane : zp);
+        const T yv = (i < kb_bwd) ? ring0[(i % RB) * NB + lane] : sign * *((i * NB + lane < n) ? y + i * NB + lane : zp);  // y holds sign * solution
         const T* tp = Av + (size_t)(i * NB) * lds + gj;
         T v[NB];
 #pragma unroll
@@ -1002,24 +1009,43 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
           const bool ok0 = g0 < n && gj < n && g0 - gj <= kd;
           v[r] = *(ok0 ? tp + r * lds : zp);
         }
-        T acc0 = T(0), acc1 = T(0);
+        T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
 #pragma unroll
-        for (int r = 0; r < NB; r += 2) {
+        for (int r = 0; r < NB; r += 4) {
           acc0 += v[r] * __shfl_sync(FULL, yv, r);
           acc1 += v[r + 1] * __shfl_sync(FULL, yv, r + 1);
+          acc2 += v[r + 2] * __shfl_sync(FULL, yv, r + 2);
+          acc3 += v[r + 3] * __shfl_sync(FULL, yv, r + 3);
         }
-        slots0[((size_t)(km & 1) * bt + s) * NB + lane] = sign * (acc0 + acc1);  // y holds sign * solution
+        slots0[((size_t)(km & 1) * bt + s) * NB + lane] = (acc0 + acc1) + (acc2 + acc3);  // the ring holds the solution itself (unsigned)
+        // the tile this warp will need two steps from now (factored milliseconds ago, possibly evicted): pull it into L2
+        if (km >= 2 && (i - 2) * NB + lane < n) {
+          const T* pf = Av + (size_t)((i - 2) * NB + lane) * lds + (km0 - 2 * NB);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + NB - 1));
+        }
       }
     }
     if (rank == 0 && warp >= 4) {
       const int p = km & 1;
-      for (int idx = (warp - 4) * 32 + lane; idx < NB * NB; idx += 4 * 32) {
-        const int r = idx >> 5, c = idx & 31, gi = km0 + NB + r, gj = km0 + c;
+      // all 16 loads of a thread in flight together (a rolled loop with the shared stores in between serialised
+      // eight L2 round trips: 1.9 us per step, the longest leg of the whole backward step)
+      T lv[NB * NB / 128], wv[NB * NB / 128];
+#pragma unroll
+      for (int q = 0; q < NB * NB / 128; ++q) {
+        const int idx = (warp - 4) * 32 + lane + 128 * q, r = idx >> 5, c = idx & 31, gi = km0 + NB + r, gj = km0 + c;
         const bool ok = gi < n && gj < n && gi - gj <= kd;
-        sm.sLk[p][r][c] = *(ok ? (Av + (size_t)gi * lds + gj) : zp);
-        sm.sWk[p][r][c] = Wbuf[(size_t)km * NB * NB + idx];
+        lv[q] = *(ok ? (Av + (size_t)gi * lds + gj) : zp);
+        wv[q] = Wbuf[(size_t)km * NB * NB + idx];
       }
-      if (warp == 4) sm.sw[p][lane] = *((km0 + lane < n) ? rhs + km0 + lane : zp);
+      const T swv = (warp == 4) ? *((km0 + lane < n) ? rhs + km0 + lane : zp) : T(0);
+#pragma unroll
+      for (int q = 0; q < NB * NB / 128; ++q) {
+        const int idx = (warp - 4) * 32 + lane + 128 * q, r = idx >> 5, c = idx & 31;
+        sm.sLk[p][r][c] = lv[q];
+        sm.sWk[p][r][c] = wv[q];
+      }
+      if (warp == 4) sm.sw[p][lane] = swv;
     }
   };
   stage(kb_bwd - 1);
@@ -1029,29 +1055,44 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
     if (rank == 0 && warp == 0) {
       const int p = k & 1, k0 = k * NB;
       const int nfar = min(nt - 1, k + bt) - (k + 2) + 1;
-      T b0 = sm.sw[p][lane], b1 = T(0);
-      for (int s = 0; s < nfar; ++s) b0 -= slots[((size_t)p * bt + s) * NB + lane];
+      T b0 = sm.sw[p][lane], b1 = T(0), b2 = T(0), b3 = T(0);
+      int s = 0;
+      for (; s + 4 <= nfar; s += 4) {
+        b0 -= slots[((size_t)p * bt + s) * NB + lane]; b1 -= slots[((size_t)p * bt + s + 1) * NB + lane];
+        b2 -= slots[((size_t)p * bt + s + 2) * NB + lane]; b3 -= slots[((size_t)p * bt + s + 3) * NB + lane];
+      }
+      for (; s < nfar; ++s) b0 -= slots[((size_t)p * bt + s) * NB + lane];
       if (k + 1 < nt) {
 #pragma unroll 8
-        for (int r = 0; r < NB; r += 2) {
+        for (int r = 0; r < NB; r += 4) {
           b0 -= sm.sLk[p][r][lane] * __shfl_sync(FULL, yprev, r);
           b1 -= sm.sLk[p][r + 1][lane] * __shfl_sync(FULL, yprev, r + 1);
+          b2 -= sm.sLk[p][r + 2][lane] * __shfl_sync(FULL, yprev, r + 2);
+          b3 -= sm.sLk[p][r + 3][lane] * __shfl_sync(FULL, yprev, r + 3);
         }
       }
-      const T b = b0 + b1;
-      T y0 = T(0), y1 = T(0);
+      const T b = (b0 + b1) + (b2 + b3);
+      T y0 = T(0), y1 = T(0), y2 = T(0), y3 = T(0);
 #pragma unroll 8
-      for (int m = 0; m < NB; m += 2) {
+      for (int m = 0; m < NB; m += 4) {
         y0 += sm.sWk[p][m][lane] * __shfl_sync(FULL, b, m);
         y1 += sm.sWk[p][m + 1][lane] * __shfl_sync(FULL, b, m + 1);
+        y2 += sm.sWk[p][m + 2][lane] * __shfl_sync(FULL, b, m + 2);
+        y3 += sm.sWk[p][m + 3][lane] * __shfl_sync(FULL, b, m + 3);
       }
-      yprev = (k0 + lane < n) ? (y0 + y1) : T(0);
-      if (k0 + lane < n) y[k0 + lane] = sign * yprev;
-    } else if (k > 0) {
-      stage(k - 1);
+      yprev = (k0 + lane < n) ? ((y0 + y1) + (y2 + y3)) : T(0);
+      ring[(k % RB) * NB + lane] = yprev;
+      TICKT(0, 8)
+    } else {
+      // the block solved in the previous step goes to global memory now: its store has a whole step to complete
+      if (rank == 0 && warp == 1 && k + 1 < kb_bwd && (k + 1) * NB + lane < n) y[(k + 1) * NB + lane] = sign * ring[((k + 1) % RB) * NB + lane];
+      if (k > 0) stage(k - 1);
+      TICKT(32, 11)
     }
     cluster.sync();
+    TICKT(0, 9) TICKT(32, 12)
   }
+  if (rank == 0 && warp == 1 && kb_bwd > 0 && lane < n) y[lane] = sign * ring[lane];   // block 0
   TICK(5)
   if (dbg && rank == C - 1 && tid == 128) for (int i = 0; i < 8; ++i) dbg[i] = sm.tc[i];   // an update CTA
   if (dbg && rank == 0 && tid == 0) for (int i = 8; i < 16; ++i) dbg[i] = sm.tc[i];          // chain CTA 0: warp 0 / warp 1 ticks

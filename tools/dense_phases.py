@@ -12,3 +12,5 @@ names = ["-", "upd CTA: loop top", "upd CTA: (chain skipped)", "upd CTA: block p
 nt = (9 * p.N + 31) // 32
 for n, v in zip(names, c):
     print(f"{n:42s} {v:12d} cycles  = {v/1.9e3:9.1f} us total, {v/1.9e3/nt:6.2f} us/panel")
+
+print("backward launch (last kernel): CTA 0 warp 0 chain %.2f us/step, its barrier wait %.2f; CTA 0 warp 1 stage %.2f us/step, its barrier wait %.2f" % tuple(c[i] / 1.965e3 / 253 for i in (8, 9, 11, 12)))
