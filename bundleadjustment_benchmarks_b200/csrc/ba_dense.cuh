@@ -571,7 +571,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
   // the register factorisation took 6.4 us instead of 2.7 us per panel next to an update team, profiles/)
   // row tiles live on the six warps that do not share an SMSP with the factoring warp 0 (warps 1-3, 5-7);
   // warp 4 (same SMSP as warp 0) only forms W_k, after the factorisation
-  const int ROWW = (roww_arg == 3) ? 3 : CL_WARPS - 2;  // 3: warps 1-3 only (one row warp per SMSP, more chain CTAs)
+  const int ROWW = ((roww_arg & 0xff) == 3) ? 3 : CL_WARPS - 2;  // 3: warps 1-3 only (one row warp per SMSP, more chain CTAs)
+  // W_k = L_kk^-1 is only needed by the backward pass: formed AFTER the factorisation (bit 8), so that its warp does not
+  // share SMSP 0 with the factor warp while the pivot chain runs; bit 9: the row-tile substitutions start after the
+  // factorisation too (experiment)
+  const bool w_after = (roww_arg & 0x100) != 0, rows_after = (roww_arg & 0x200) != 0;
   const int NC = min(max(1, (ROWW == 3) ? C / 2 : C / 4), (bt + ROWW - 1) / ROWW);
   int* const work0 = cluster.map_shared_rank(&sm.work[0], 0);
 #ifdef BA_DENSE_TICKS
@@ -794,6 +798,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
           }
         }
         pre = false;
+        if ((do_w && w_after) || (!do_w && rows_after)) { while (ld_acquire_cta(&sm.pn.progress) < NB) {} }
         // one substitution call site (code size). W mode: identity rows, x[c] = W(c, lane), un-scaled, straight to
         // Wbuf. Tile mode: X L_kk^T = A_ik, L_ik = X D^-1 into the warp's tile buffer (row = lane), then written
         // out with coalesced 16-byte stores; g_i -= L_ik z_k.
@@ -963,7 +968,106 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_band_ldlt_cluster(const LdltJ
   // Iteration k: chain(k+1) (which first gives column k+1 panel k's update) runs next to the update of
   // the columns >= k+2 with panel k; the chain team joins the update when it is done.
   __syncthreads();
-  if (P.do_fwd) {
+  if (P.do_fwd == 2) {
+    // ---------------------------------------------------------------- forward substitution with the EXISTING factor
+    // (refinement solves of the QR variants: S is already factored, only a new right-hand side comes in): z = L^-1 g on the
+    // panels [0, np_fwd), rhs <- D^-1 z there, g_i -= sum_k L(i,k) z_k on the rows below. Mirror image of the backward pass:
+    // z_k = W_k (g_k - sum_{i<k} L(k,i) z_i); the far tiles (k, i), i <= k-2, are reduced one step ahead by all CTAs into
+    // CTA 0 through DSMEM, the chain (CTA 0, warp 0) is two 32x32 mat-vecs: the tile (k, k-1) with z_{k-1}, then W_k.
+    T* fslots = &sm.gA[0][0][0][0][0];                  // [2][bt][NB]
+    T* fslots0 = cluster.map_shared_rank(fslots, 0);
+    constexpr int FRB = 256;
+    T* fring = &sm.gB[0][0][0][0][0];                   // z_k ring in CTA 0
+    const T* fring0 = cluster.map_shared_rank(fring, 0);
+    auto row_tile_times_z = [&](const int ti, const int tk) -> T {   // lane = row: sum_c L(32 ti + lane, 32 tk + c) z_tk[c]
+      const int gi = ti * NB + lane;
+      const T zv = fring0[(tk % FRB) * NB + lane];
+      const T* tp = Av + (size_t)gi * lds + tk * NB;
+      T v[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) { const bool ok = gi < n && gi - (tk * NB + c) <= kd; v[c] = *(ok ? tp + c : zp); }
+      T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+#pragma unroll
+      for (int c = 0; c < NB; c += 4) {
+        a0 += v[c] * __shfl_sync(FULL, zv, c); a1 += v[c + 1] * __shfl_sync(FULL, zv, c + 1);
+        a2 += v[c + 2] * __shfl_sync(FULL, zv, c + 2); a3 += v[c + 3] * __shfl_sync(FULL, zv, c + 3);
+      }
+      return (a0 + a1) + (a2 + a3);
+    };
+    auto fstage = [&](const int km) {                   // everything step km needs except z_{km-1}
+      const int lo = max(0, km - bt);
+      const int nfar = (km - 2) - lo + 1;               // tiles (km, i), i = km-2 .. lo
+      if (warp >= 1 && warp <= 3) {
+        for (int sI = rank + C * (warp - 1); sI < nfar; sI += C * 3)
+          fslots0[((size_t)(km & 1) * bt + sI) * NB + lane] = row_tile_times_z(km, km - 2 - sI);
+      }
+      if (rank == 0 && warp >= 4) {
+        const int p = km & 1, km0 = km * NB;
+        T lv[NB * NB / 128], wv[NB * NB / 128];
+#pragma unroll
+        for (int q = 0; q < NB * NB / 128; ++q) {
+          const int idx = (warp - 4) * 32 + lane + 128 * q, r = idx >> 5, c = idx & 31, gi = km0 + r, gj = km0 - NB + c;
+          const bool ok = km > 0 && gi < n && gi - gj <= kd;
+          lv[q] = *(ok ? (Av + (size_t)gi * lds + gj) : zp);
+          wv[q] = Wbuf[(size_t)km * NB * NB + idx];
+        }
+        const T swv = (warp == 4) ? *((km0 + lane < n) ? rhs + km0 + lane : zp) : T(0);
+#pragma unroll
+        for (int q = 0; q < NB * NB / 128; ++q) {
+          const int idx = (warp - 4) * 32 + lane + 128 * q, r = idx >> 5, c = idx & 31;
+          sm.sLk[p][r][c] = lv[q];
+          sm.sWk[p][r][c] = wv[q];
+        }
+        if (warp == 4) sm.sw[p][lane] = swv;
+      }
+    };
+    if (np_fwd > 0) fstage(0);
+    cluster.sync();
+    T zprev = T(0);
+    for (int k = 0; k < np_fwd; ++k) {
+      if (rank == 0 && warp == 0) {
+        const int p = k & 1, lo = max(0, k - bt), nfar = (k - 2) - lo + 1;
+        T b0 = sm.sw[p][lane], b1 = T(0), b2 = T(0), b3 = T(0);
+        for (int sI = 0; sI < nfar; ++sI) b0 -= fslots[((size_t)p * bt + sI) * NB + lane];
+        if (k > 0) {
+#pragma unroll 8
+          for (int c = 0; c < NB; c += 4) {
+            b0 -= sm.sLk[p][lane][c] * __shfl_sync(FULL, zprev, c);
+            b1 -= sm.sLk[p][lane][c + 1] * __shfl_sync(FULL, zprev, c + 1);
+            b2 -= sm.sLk[p][lane][c + 2] * __shfl_sync(FULL, zprev, c + 2);
+            b3 -= sm.sLk[p][lane][c + 3] * __shfl_sync(FULL, zprev, c + 3);
+          }
+        }
+        const T b = (b0 + b1) + (b2 + b3);
+        T z0 = T(0), z1 = T(0), z2 = T(0), z3 = T(0);
+#pragma unroll 8
+        for (int m = 0; m < NB; m += 4) {
+          z0 += sm.sWk[p][lane][m] * __shfl_sync(FULL, b, m);
+          z1 += sm.sWk[p][lane][m + 1] * __shfl_sync(FULL, b, m + 1);
+          z2 += sm.sWk[p][lane][m + 2] * __shfl_sync(FULL, b, m + 2);
+          z3 += sm.sWk[p][lane][m + 3] * __shfl_sync(FULL, b, m + 3);
+        }
+        zprev = (k * NB + lane < n) ? ((z0 + z1) + (z2 + z3)) : T(0);
+        fring[(k % FRB) * NB + lane] = zprev;
+      } else {
+        // D^-1 z of the block solved in the previous step goes to global memory now (a whole step to complete)
+        if (rank == 0 && warp == 1 && k >= 1 && (k - 1) * NB + lane < n) rhs[(k - 1) * NB + lane] = fring[((k - 1) % FRB) * NB + lane] / dvec[(k - 1) * NB + lane];
+        if (k + 1 < np_fwd) fstage(k + 1);
+      }
+      cluster.sync();
+    }
+    if (rank == 0 && warp == 1 && np_fwd > 0 && (np_fwd - 1) * NB + lane < n)
+      rhs[(np_fwd - 1) * NB + lane] = fring[((np_fwd - 1) % FRB) * NB + lane] / dvec[(np_fwd - 1) * NB + lane];
+    // rows below the eliminated panels: g_i -= sum_k L(i, k) z_k, one warp per row tile (fixed order over k)
+    const int ilast = min(nt - 1, np_fwd - 1 + bt);
+    for (int i = np_fwd + rank * CL_WARPS + warp; i <= ilast; i += C * CL_WARPS) {
+      T acc = T(0);
+      for (int kk = max(0, i - bt); kk < np_fwd; ++kk) acc += row_tile_times_z(i, kk);
+      if (i * NB + lane < n) rhs[i * NB + lane] -= acc;
+    }
+    cluster.sync();
+  }
+  if (P.do_fwd == 1) {
     if (rank < NC && np_fwd > 0) chain(0);
     cluster.sync();
     for (int k = 0; k < np_fwd; ++k) {
@@ -1129,6 +1233,16 @@ __global__ void k_band_combine(BandMat<T> A, T* __restrict__ g, const T* __restr
     A.v[(size_t)i * lds + j] += Rv[(size_t)(n - 1 - j) * lds + (n - 1 - i)];
   }
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < (size_t)nm; t += stride) g[r0 + t] += gr[n - 1 - (r0 + (int)t)];
+}
+// right-hand side only (solves with an existing two-sided factor): g'(i') = g(n-1-i') on the rows of the reversed system
+// outside the middle block, 0 inside; and g(i) += g'(n-1-i) on the middle rows
+template <class T>
+__global__ void k_rhs_reverse(const T* __restrict__ g, T* __restrict__ gr, int n, int np, int mrow0) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) gr[i] = (i < mrow0) ? g[n - 1 - i] : T(0);
+}
+template <class T>
+__global__ void k_rhs_combine(T* __restrict__ g, const T* __restrict__ gr, int n, int r0, int nm) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nm; t += gridDim.x * blockDim.x) g[r0 + t] += gr[n - 1 - (r0 + t)];
 }
 // dst[i] = src[n-1-i] for i in [i0, i1)  (dst and src indexed from their own origins: dst_off/src_off)
 template <class T>

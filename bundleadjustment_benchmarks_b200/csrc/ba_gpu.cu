@@ -281,7 +281,7 @@ struct Impl : ba_handle {
   // QRKIT / MOREQR right block: LDL^T of S + corrected semi-normal refinement through J2bot (k_csne_*), or (BA_QR_HOUSEHOLDER=1)
   // the Householder QR of the square S of round 1
   bool qr_csne = false; int csne_steps = 1, nlong = 0;
-  DevBuf<T> d_keepS, d_u, d_delta;
+  DevBuf<T> d_u, d_delta;
   DevBuf<int> d_long_pt;
   int nblocks = 0, gather_grid = 0;
   DevBuf<T> d_meas, d_cams, d_cams_test, d_X, d_X_test, d_dx_pt, d_dx_cam, d_red /* S band | g | gJ */, d_keep, d_dvec, d_tmp;
@@ -330,7 +330,7 @@ struct Impl : ba_handle {
     CK(d_red.alloc(red_count + 2 * (size_t)n));
     CK(d_dvec.alloc((size_t)n + NB));  // D is read/written in whole 32-wide panels
     if (keep_reduced) CK(d_keep.alloc(red_count + n));
-    if (qr_csne) { CK(d_keepS.alloc(red_count)); CK(d_delta.alloc(n)); }
+    if (qr_csne) CK(d_delta.alloc(n));
     d_qr.free();
     return BA_OK;
   }
@@ -521,6 +521,8 @@ struct Impl : ba_handle {
     if (const char* cs = std::getenv("BA_CLUSTER_SIZE")) cluster_size = std::max(1, std::min(16, atoi(cs)));
     if (std::getenv("BA_FORCE_GRID_LDLT")) force_grid_ldlt = true;
     if (const char* rw = std::getenv("BA_LDLT_ROWW")) ldlt_roww = atoi(rw) == 3 ? 3 : 6;
+    if (const char* wa = std::getenv("BA_LDLT_W_AFTER")) { if (atoi(wa) != 0) ldlt_roww |= 0x100; }
+    if (const char* ra = std::getenv("BA_LDLT_ROWS_AFTER")) { if (atoi(ra) != 0) ldlt_roww |= 0x200; }
     if (const char* ts = std::getenv("BA_LDLT_TWOSIDED")) two_sided = atoi(ts) != 0;
     if (const char* v2 = std::getenv("BA_LDLT_V2")) ldlt_v2 = atoi(v2) != 0;
     CK(cudaFuncSetAttribute(k_band_ldlt_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ldlt2Smem)));
@@ -727,7 +729,6 @@ struct Impl : ba_handle {
       if (d_keep.n < red_count + n) CK(d_keep.alloc(red_count + n));
       CK(cudaMemcpyAsync(d_keep.p, d_red.p, (red_count + n) * sizeof(T), cudaMemcpyDeviceToDevice, stream));
     }
-    if (qr_csne && csne_steps > 0) CK(cudaMemcpyAsync(d_keepS.p, d_red.p, red_count * sizeof(T), cudaMemcpyDeviceToDevice, stream));  // S again for the refinement solve
     mark(3);
     { int rc = factor_reduced(); if (rc) return rc; }
     mark(4);
@@ -742,9 +743,12 @@ struct Impl : ba_handle {
   static cudaError_t launch_fwd2_impl(const cudaLaunchConfig_t&, const LdltJob<float>&, long long*) { return cudaErrorNotSupported; }
 
   // factorisation of the reduced camera block in d_red (LDL^T or Householder QR of S)
-  int factor_reduced() {
+  // solve_only: S is already factored (same handle, same band), only a new right-hand side sits in gvec(): forward
+  // substitution with the existing factor (do_fwd = 2) instead of factorisation + folded forward substitution
+  int factor_reduced(bool solve_only = false) {
     if (variant == BA_QRCHOL || variant == BA_CHOLESKY || qr_csne) {
-      CK(cudaMemsetAsync(d_info.p, 0, sizeof(int), stream));
+      if (!solve_only) CK(cudaMemsetAsync(d_info.p, 0, sizeof(int), stream));
+      const int fwd = solve_only ? 2 : 1;
       BandMat<T> A = band();
       const int nt = (n + NB - 1) / NB, bt = (kd + NB - 1) / NB;
       const double flops = (double)n * kd * kd;
@@ -779,7 +783,7 @@ struct Impl : ba_handle {
         if (!two_sided || q < bt + 2) {
           LdltJob<T> job = {};
           job.sign = T(-1);
-          job.p[0] = LdltProblem<T>{A, d_dvec.p, d_W.p, gvec(), d_dx_cam.p, d_info.p, nt, nt, 1, 1};
+          job.p[0] = LdltProblem<T>{A, d_dvec.p, d_W.p, gvec(), d_dx_cam.p, d_info.p, nt, nt, fwd, 1};
           CK(launch(job, 1));
         } else {
           // Two-sided (twisted) factorisation: the chain of n dependent pivots is cut in two. Cluster 0 eliminates rows
@@ -798,17 +802,19 @@ struct Impl : ba_handle {
           BandMat<T> Ar{Rv, lds(), np, kd};
           BandMat<T> Am{Sv() + (size_t)r0 * ldsv + r0, lds(), nm, std::min(kd, nm - 1)};
           const int ab = 4 * sm_count;
-          k_band_reverse<T><<<ab, 256, 0, stream>>>(A, gvec(), Rv, gr, np, q * NB);
+          if (solve_only) k_rhs_reverse<T><<<64, 256, 0, stream>>>(gvec(), gr, n, np, q * NB);
+          else k_band_reverse<T><<<ab, 256, 0, stream>>>(A, gvec(), Rv, gr, np, q * NB);
           LdltJob<T> job = {};
           job.sign = T(-1);
-          job.p[0] = LdltProblem<T>{A, d_dvec.p, d_W.p, gvec(), d_dx_cam.p, d_info.p, q, 0, 1, 0};
-          job.p[1] = LdltProblem<T>{Ar, d_dvec2.p, d_W2.p, gr, d_y2.p, d_info.p, q, 0, 1, 0};
-          if (ldlt_v2 && sizeof(T) == 8 && cluster_size == 16 && bt <= L2_MAX_BT) CK(launch_fwd2(job));
+          job.p[0] = LdltProblem<T>{A, d_dvec.p, d_W.p, gvec(), d_dx_cam.p, d_info.p, q, 0, fwd, 0};
+          job.p[1] = LdltProblem<T>{Ar, d_dvec2.p, d_W2.p, gr, d_y2.p, d_info.p, q, 0, fwd, 0};
+          if (!solve_only && ldlt_v2 && sizeof(T) == 8 && cluster_size == 16 && bt <= L2_MAX_BT) CK(launch_fwd2(job));
           else CK(launch(job, 2));
-          k_band_combine<T><<<64, 256, 0, stream>>>(A, gvec(), Rv, gr, r0, nm);
+          if (solve_only) k_rhs_combine<T><<<8, 256, 0, stream>>>(gvec(), gr, n, r0, nm);
+          else k_band_combine<T><<<64, 256, 0, stream>>>(A, gvec(), Rv, gr, r0, nm);
           LdltJob<T> mid = {};
           mid.sign = T(-1);
-          mid.p[0] = LdltProblem<T>{Am, d_dvec.p + r0, d_WM.p, gvec() + r0, d_dx_cam.p + r0, d_info.p, ntm, ntm, 1, 1};
+          mid.p[0] = LdltProblem<T>{Am, d_dvec.p + r0, d_WM.p, gvec() + r0, d_dx_cam.p + r0, d_info.p, ntm, ntm, fwd, 1};
           CK(launch(mid, 1));
           k_flip_copy<T><<<8, 256, 0, stream>>>(d_y2.p, d_dx_cam.p, n, q * NB, np);  // y'(i') = y(n-1-i') on the middle rows
           job.p[0].do_fwd = 0; job.p[0].do_bwd = 1; job.p[0].kb_bwd = q;
@@ -824,7 +830,7 @@ struct Impl : ba_handle {
         void* args[] = {&A, &dv, &info};
         const int useful = std::max(1, std::min(bt, nt) * (std::min(bt, nt) + 1) / 2);
         const int grid = std::max(1, std::min(coop_grid, useful));
-        CK(cudaLaunchCooperativeKernel((void*)k_band_ldlt<T>, dim3(grid), dim3(DENSE_THREADS), args, 0, stream));
+        if (!solve_only) CK(cudaLaunchCooperativeKernel((void*)k_band_ldlt<T>, dim3(grid), dim3(DENSE_THREADS), args, 0, stream));
         solved_in_factor = false;
       }
       launches++;
@@ -905,7 +911,7 @@ struct Impl : ba_handle {
   }
 
   // QRKIT / MOREQR: corrected semi-normal refinement of dx_cam = -y0 (see k_csne_point): r = J2bot^T (d - J2bot y0) through
-  // the D records, S delta = r with the kept copy of S, dx_cam -= delta
+  // the D records, S delta = r by forward + backward substitution with the factor of S already in place, dx_cam -= delta
   int csne_refine(T lamT) {
     const T sl = (T)std::sqrt(lamT);
     const T diag = sl * sl;
@@ -916,9 +922,8 @@ struct Impl : ba_handle {
       launches += 2 + (nlong ? 1 : 0);
       CK(cudaGetLastError());
       if (comm) NK(g_nccl.AllReduce(gvec(), gvec(), (size_t)n, nccl_t(), ncclSum, comm, stream));
-      CK(cudaMemcpyAsync(d_red.p, d_keepS.p, red_count * sizeof(T), cudaMemcpyDeviceToDevice, stream));
       std::swap(d_dx_cam.p, d_delta.p);                 // the solvers write -S^-1 rhs into d_dx_cam
-      int rc = factor_reduced();
+      int rc = factor_reduced(true);                    // S is factored: forward + backward substitution only
       if (!rc) rc = solve_reduced();
       std::swap(d_dx_cam.p, d_delta.p);
       if (rc) return rc;
