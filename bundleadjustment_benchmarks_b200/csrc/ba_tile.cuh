@@ -1395,6 +1395,253 @@ constexpr int BIG_THREADS = 256;
 constexpr int BIG_POINT_MAX = 3000;  // 8 scalars per observation in shared memory (192 KB in double)
 template <class T> constexpr size_t big_point_smem_bytes(int nmax) { return (size_t)8 * nmax * sizeof(T); }
 
+// ---- block-parallel versions of point_householder / point_normal for ONE point per CTA (long tracks: up to 3000
+// observations). Thread t owns the observations t, t + BIG_THREADS, ...; every sum over the point's rows (column norms,
+// reflector dots, Q1^T e, Jp^T e, the 3x3 normal equations) is a fixed-order block reduction whose result every thread
+// receives, so the 3x3 R, the reflector scalars and the sqrt(lambda) I3 rows are simply replicated in all threads (as in
+// the warp-segmented kernel). Round 1 ran the factorisation of such a point on one thread.
+template <class T, int NV>
+__device__ __forceinline__ void big_block_sum(T (&v)[NV], T* red /* [BIG_THREADS / 32][NV] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
+  }
+  __syncthreads();                       // previous use of `red` is over
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) red[warp * NV + q] = v[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    T s = T(0);
+#pragma unroll
+    for (int w = 0; w < BIG_THREADS / 32; ++w) s += red[w * NV + q];
+    v[q] = s;
+  }
+}
+
+template <class T>
+__device__ void big_point_householder(BigPointStore<T>& st, const int n, const T sl, T* red) {
+  const int t = threadIdx.x, S = st.st;
+  const T tiny = (sizeof(T) == 8 ? T(2.2250738585072014e-308) : T(1.17549435e-38f));
+  T L[3][3] = {{sl, T(0), T(0)}, {T(0), sl, T(0)}, {T(0), T(0), sl}};
+  T tau[3];
+  int pmv[3] = {0, 1, 2};
+  auto Q = [&](int a, int b, int i) -> T& { return st.Q[(size_t)(3 * a + b) * S + i]; };
+  {  // G = Jp^T e in the original column order
+    T g[3] = {T(0), T(0), T(0)};
+    for (int i = t; i < n; i += BIG_THREADS) {
+      const T e0 = st.E[i], e1 = st.E[S + i];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) g[b] += Q(0, b, i) * e0 + Q(1, b, i) * e1;
+    }
+    big_block_sum<T, 3>(g, red);
+    if (t == 0) { st.G[0] = g[0]; st.G[1] = g[1]; st.G[2] = g[2]; }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    // squared norms of the remaining columns over rows >= k (row rho = 2 i + a)
+    T nn[3] = {T(0), T(0), T(0)};
+    for (int i = t; i < n; i += BIG_THREADS) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        if (2 * i + a >= k) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) if (c >= k) { const T v = Q(a, c, i); nn[c] += v * v; }
+        }
+      }
+    }
+    big_block_sum<T, 3>(nn, red);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c >= k) nn[c] += L[0][c] * L[0][c] + L[1][c] * L[1][c] + L[2][c] * L[2][c];
+    int best = k;
+    T bestv = nn[k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c > k && nn[c] > bestv) { best = c; bestv = nn[c]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c > k) {
+        const bool sw = best == c;
+        if (sw) {
+          for (int i = t; i < n; i += BIG_THREADS) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a) { const T x = Q(a, k, i); Q(a, k, i) = Q(a, c, i); Q(a, c, i) = x; }
+          }
+        }
+        cswap(L[0][k], L[0][c], sw); cswap(L[1][k], L[1][c], sw); cswap(L[2][k], L[2][c], sw);
+        const int x = pmv[k]; pmv[k] = sw ? pmv[c] : pmv[k]; pmv[c] = sw ? x : pmv[c];
+      }
+    }
+    __syncthreads();
+    // row k lives in observation k >> 1, slot k & 1
+    const T c0 = Q(k & 1, k, k >> 1);
+    T akc[3] = {T(0), T(0), T(0)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c > k) akc[c] = Q(k & 1, c, k >> 1);
+    T sums[3] = {T(0), T(0), T(0)};   // tail2, dot with column k+1, dot with column k+2 (rows > k)
+    for (int i = t; i < n; i += BIG_THREADS) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        if (2 * i + a > k) {
+          const T v = Q(a, k, i);
+          sums[0] += v * v;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) if (c > k) sums[c - k] += v * Q(a, c, i);
+        }
+      }
+    }
+    big_block_sum<T, 3>(sums, red);
+    const T tail2 = sums[0] + L[0][k] * L[0][k] + L[1][k] * L[1][k] + L[2][k] * L[2][k];
+    const bool degenerate = tail2 <= tiny;
+    T beta = tsqrt(c0 * c0 + tail2);
+    if (c0 >= T(0)) beta = -beta;
+    if (degenerate) beta = c0;
+    const T inv = degenerate ? T(0) : T(1) / (c0 - beta);
+    const T tk = degenerate ? T(0) : (beta - c0) / beta;
+    tau[k] = tk;
+    // the dots were taken with the UN-scaled column k: v_r = A[r][k] inv
+    T sd[3] = {T(0), T(0), T(0)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c > k) sd[c] = (akc[c] + inv * sums[c - k] + inv * (L[0][k] * L[0][c] + L[1][k] * L[1][c] + L[2][k] * L[2][c])) * tk;
+    for (int i = t; i < n; i += BIG_THREADS) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int rho = 2 * i + a;
+        if (rho > k) {
+          const T v = Q(a, k, i) * inv;
+          Q(a, k, i) = v;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) if (c > k) Q(a, c, i) -= sd[c] * v;
+        } else if (rho == k) {
+          Q(a, k, i) = beta;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) if (c > k) Q(a, c, i) -= sd[c];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c > k) { L[0][c] -= sd[c] * (L[0][k] * inv); L[1][c] -= sd[c] * (L[1][k] * inv); L[2][c] -= sd[c] * (L[2][k] * inv); }
+    }
+    L[0][k] *= inv; L[1][k] *= inv; L[2][k] *= inv;
+    __syncthreads();
+  }
+  if (t == 0) {  // R sits in rows 0..2 (observation 0: rows 0, 1; observation 1: row 2), already in pivoted column order
+    st.Rm[0] = Q(0, 0, 0); st.Rm[1] = Q(0, 1, 0); st.Rm[2] = Q(0, 2, 0);
+    st.Rm[3] = Q(1, 1, 0); st.Rm[4] = Q(1, 2, 0); st.Rm[5] = Q(0, 2, 1);
+    st.perm[0] = pmv[0] | (pmv[1] << 2) | (pmv[2] << 4);
+  }
+  __syncthreads();
+  // form the thin Q1 in place (dorg2r): k = 2, 1, 0
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    const T tk = tau[k];
+    T akc[3] = {T(0), T(0), T(0)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c > k) akc[c] = Q(k & 1, c, k >> 1);
+    T dots[2] = {T(0), T(0)};
+    for (int i = t; i < n; i += BIG_THREADS) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        if (2 * i + a > k) {
+          const T v = Q(a, k, i);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) if (c > k) dots[c - k - 1] += v * Q(a, c, i);
+        }
+      }
+    }
+    big_block_sum<T, 2>(dots, red);
+    T sd[3] = {T(0), T(0), T(0)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c > k) sd[c] = (akc[c] + dots[c - k - 1] + L[0][k] * L[0][c] + L[1][k] * L[1][c] + L[2][k] * L[2][c]) * tk;
+    for (int i = t; i < n; i += BIG_THREADS) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int rho = 2 * i + a;
+        if (rho > k) {
+          const T v = Q(a, k, i);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) if (c > k) Q(a, c, i) -= sd[c] * v;
+          Q(a, k, i) = -tk * v;
+        } else if (rho == k) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) if (c > k) Q(a, c, i) -= sd[c];
+          Q(a, k, i) = T(1) - tk;
+        } else {
+          Q(a, k, i) = T(0);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c > k) { L[0][c] -= sd[c] * L[0][k]; L[1][c] -= sd[c] * L[1][k]; L[2][c] -= sd[c] * L[2][k]; }
+    }
+    L[0][k] *= -tk; L[1][k] *= -tk; L[2][k] *= -tk;
+    __syncthreads();
+  }
+  T cq[3] = {T(0), T(0), T(0)};
+  for (int i = t; i < n; i += BIG_THREADS) {
+    const T e0 = st.E[i], e1 = st.E[S + i];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) cq[b] += Q(0, b, i) * e0 + Q(1, b, i) * e1;
+  }
+  big_block_sum<T, 3>(cq, red);
+  if (t == 0) { st.C[0] = cq[0]; st.C[1] = cq[1]; st.C[2] = cq[2]; }
+  __syncthreads();
+}
+
+// normal-equation point factor (CHOLESKY variant), one point per CTA
+template <class T>
+__device__ void big_point_normal(BigPointStore<T>& st, const int n, const T lambda, T* red) {
+  const int t = threadIdx.x, S = st.st;
+  auto Q = [&](int a, int b, int i) -> T& { return st.Q[(size_t)(3 * a + b) * S + i]; };
+  T v[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, g[3] = {T(0), T(0), T(0)};
+  for (int i = t; i < n; i += BIG_THREADS) {
+    const T e0 = st.E[i], e1 = st.E[S + i];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const T x0 = Q(a, 0, i), x1 = Q(a, 1, i), x2 = Q(a, 2, i), e = a ? e1 : e0;
+      v[0] += x0 * x0; v[1] += x1 * x0; v[2] += x1 * x1; v[3] += x2 * x0; v[4] += x2 * x1; v[5] += x2 * x2;
+      g[0] += x0 * e; g[1] += x1 * e; g[2] += x2 * e;
+    }
+  }
+  big_block_sum<T, 6>(v, red);
+  big_block_sum<T, 3>(g, red);
+  const T v00 = v[0] + lambda, v10 = v[1], v11 = v[2] + lambda, v20 = v[3], v21 = v[4], v22 = v[5] + lambda;
+  const T d0 = v00, l10 = v10 / d0, l20 = v20 / d0;
+  const T d1 = tmax(v11 - l10 * l10 * d0, lambda), l21 = (v21 - l20 * l10 * d0) / d1;   // pivot floor: see point_normal
+  const T d2 = tmax(v22 - l20 * l20 * d0 - l21 * l21 * d1, lambda);
+  const T q0 = tsqrt(d0), q1 = tsqrt(d1), q2 = tsqrt(d2);
+  const T R[6] = {q0, q0 * l10, q0 * l20, q1, q1 * l21, q2};
+  const T i00 = T(1) / R[0], i11 = T(1) / R[3], i22 = T(1) / R[5];
+  T cq[3] = {T(0), T(0), T(0)};
+  for (int i = t; i < n; i += BIG_THREADS) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const T y0 = Q(a, 0, i) * i00;
+      const T y1 = (Q(a, 1, i) - y0 * R[1]) * i11;
+      const T y2 = (Q(a, 2, i) - y0 * R[2] - y1 * R[4]) * i22;
+      Q(a, 0, i) = y0; Q(a, 1, i) = y1; Q(a, 2, i) = y2;
+      const T e = st.E[(size_t)a * S + i];
+      cq[0] += y0 * e; cq[1] += y1 * e; cq[2] += y2 * e;
+    }
+  }
+  big_block_sum<T, 3>(cq, red);
+  if (t == 0) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) st.Rm[q] = R[q];
+    st.perm[0] = 0 | (1 << 2) | (2 << 4);
+    st.G[0] = g[0]; st.G[1] = g[1]; st.G[2] = g[2];
+    st.C[0] = cq[0]; st.C[1] = cq[1]; st.C[2] = cq[2];
+  }
+  __syncthreads();
+}
+
 template <class T>
 __global__ void __launch_bounds__(BIG_THREADS) k_point_factor_big(TileArgs<T> a, const int* __restrict__ huge_pt, const int* __restrict__ slot,
                                                                   T* __restrict__ Prec, T* __restrict__ Drec, T* __restrict__ Ptrec) {
@@ -1415,10 +1662,9 @@ __global__ void __launch_bounds__(BIG_THREADS) k_point_factor_big(TileArgs<T> a,
     for (int k = 0; k < 6; ++k) st.Q[(size_t)k * n + i] = jp[k];
   }
   __syncthreads();
-  if (t == 0) {
-    if (a.factor == PF_HOUSEHOLDER && n >= 2) point_householder<T, BigPointStore<T>>(st, 0, 0, n, tsqrt(a.lambda));
-    else point_normal<T, BigPointStore<T>>(st, 0, 0, n, a.lambda);
-  }
+  __shared__ T bred[(BIG_THREADS / 32) * 6];
+  if (a.factor == PF_HOUSEHOLDER && n >= 2) big_point_householder<T>(st, n, tsqrt(a.lambda), bred);
+  else big_point_normal<T>(st, n, a.lambda, bred);
   __syncthreads();
   const T c0 = st.C[0], c1 = st.C[1], c2 = st.C[2];
   for (int i = t; i < n; i += BIG_THREADS) {

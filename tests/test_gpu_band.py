@@ -72,6 +72,45 @@ def test_band_solve_two_sided(n, kd):
     assert np.linalg.norm(y2 - y1) / np.linalg.norm(ref) < 1e-12
 
 
+@pytest.mark.parametrize("n,kd", [(1990, 31), (3001, 100), (2500, 257), (4100, 548), (5000, 576)])
+def test_band_solve_owner_computes_forward(n, kd):
+    """BA_LDLT_V2=1: the owner-computes forward elimination (k_band_ldlt_fwd2, ba_ldlt2.cuh: tiles resident in shared memory,
+    DMMA triangular solves, chain on the lightest CTA, DSMEM flags / hand-over) against numpy and against the first-generation
+    kernel, for 1..18 row tiles per panel (kd = 31 .. 576), band edges cutting through tiles, ragged n."""
+    A, g = band_spd(n, kd, 300 + n)
+    ref = np.linalg.solve(A, g)
+    os.environ["BA_LDLT_V2"] = "1"
+    try:
+        s2 = _solve("QRCHOL", "f64", False)
+    finally:
+        os.environ.pop("BA_LDLT_V2", None)
+    y2 = s2.debug_band_solve(A, g, kd)
+    s2.close()
+    s1 = _solve("QRCHOL", "f64", False)
+    y1 = s1.debug_band_solve(A, g, kd)
+    s1.close()
+    nr = np.linalg.norm(ref)
+    assert np.linalg.norm(y2 - ref) / nr < 1e-12 and np.linalg.norm(y2 - y1) / nr < 1e-12
+
+
+def test_solve_with_existing_factor():
+    """QR variants: the refinement correction is solved by forward + backward substitution with the factor of S already in
+    place (do_fwd = 2 of k_band_ldlt_cluster, two-sided and one-sided): QRKIT's step on a banded problem (two-sided path) and on
+    a dense one must satisfy the normal equations of the trial as well as QRCHOL's does."""
+    for prob in (bal.synthetic(400, 8000, window=10, seed=8), bal.synthetic(30, 2000, window=30, seed=9)):
+        res = {}
+        for variant in ("QRCHOL", "QRKIT"):
+            s = solver.GpuSolver(prob, variant)
+            e, cn2, _ = s.linearize()
+            lam = 1e-9 * cn2
+            s.compute(lam)
+            dxn, _, et = s.solve_try()
+            res[variant] = (s.dx(), et)
+            s.close()
+        d = np.linalg.norm(res["QRKIT"][0] - res["QRCHOL"][0]) / np.linalg.norm(res["QRCHOL"][0])
+        assert d < 1e-8 and abs(res["QRKIT"][1] - res["QRCHOL"][1]) / res["QRCHOL"][1] < 1e-11, (prob.name, d)
+
+
 def test_band_solve_indefinite_ldlt():
     """SimplicialLDLT semantics: un-pivoted LDL^T also factors symmetric indefinite matrices (D < 0 allowed)."""
     s = _solve("QRCHOL", "f64", False)
