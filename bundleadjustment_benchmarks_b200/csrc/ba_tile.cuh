@@ -673,6 +673,22 @@ template <class T> __device__ __forceinline__ void rec_cp1(T* smem_dst, const T*
 }
 __device__ __forceinline__ void rec_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void rec_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// Bulk asynchronous copy (the TMA engine's 1D mode: cp.async.bulk, UBLKCP in SASS) of a CONTIGUOUS run of records into
+// shared memory, completion signalled on an mbarrier: one instruction by one lane replaces 14 (double) 16-byte cp.async per
+// lane for a warp's 32 records. Source, destination and size must be multiples of 16 bytes (records are 224 / 112 bytes).
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(b), "r"(parity) : "memory");
+}
 // scalars [lo, hi) of a staged record into registers, 16-byte shared loads (lo, hi multiples of EPC)
 template <int LO, int HI> __device__ __forceinline__ void lds_rec(const double* s, double (&r)[REC]) {
 #pragma unroll
@@ -987,6 +1003,24 @@ __global__ void __launch_bounds__(TILE, 4) k_backsub_eval(TileArgs<T> a, const T
   // instruction moves RPI whole records; the tile's records are contiguous), so a __syncwarp suffices before
   // they are read. Every load that does not depend on staged data is issued before the wait: the kernel is a
   // chain of dependent global loads (tile -> point range -> cameras -> dx_cam) and nothing else may add a level.
+#ifdef BA_BULK_COPY
+  // Experiment kept for the record: the warp's 32 records are contiguous in global memory, so ONE bulk
+  // copy (TMA engine's 1D mode, cp.async.bulk -> UBLKCP + mbarrier) per warp can replace 14 16-byte cp.async per lane.
+  // Measured on B200 at the synthetic scale: 0.457 ms (dense copy; the 16-byte record reads at stride 224 bytes then have
+  // two-way bank conflicts) and 0.494 ms (one 224-byte bulk copy per record into the conflict-free stride) against
+  // 0.433 ms for the LDGSTS path below, which therefore stays the default.
+  constexpr int PS = REC;
+  __shared__ unsigned long long bars[TILE / 32];
+  const int wrec = min(32, nobs - w0);
+  if (wrec > 0) {
+    if (lane == 0) {
+      mbar_init(&bars[t >> 5], 1);
+      bulk_load(sP + (size_t)w0 * PS, Prec + (size_t)(o0 + w0) * REC, (unsigned)(wrec * REC * sizeof(T)), &bars[t >> 5]);
+    }
+    __syncwarp();
+  }
+#else
+  constexpr int PS = SR;
   {
     const int rsub = lane / CPR, part = lane - rsub * CPR;
     if (lane < RPI * CPR) {
@@ -997,6 +1031,7 @@ __global__ void __launch_bounds__(TILE, 4) k_backsub_eval(TileArgs<T> a, const T
       }
     }
   }
+#endif
   int cam_idx = 0, lp = 0;
   if (t < nobs) { cam_idx = __ldg(a.view + o0 + t); lp = __ldg(a.point + o0 + t) - p0; }
   {
@@ -1030,10 +1065,13 @@ __global__ void __launch_bounds__(TILE, 4) k_backsub_eval(TileArgs<T> a, const T
   }
   load_cam<T>(cams_test, cam_idx, cam);
   rec_wait<0>();
+#ifdef BA_BULK_COPY
+  if (wrec > 0) mbar_wait(&bars[t >> 5], 0);
+#endif
   __syncwarp();
   if (t < nobs) {
     T r[REC], d[9];
-    lds_rec<0, REC>(sP + (size_t)t * SR, r);
+    lds_rec<0, REC>(sP + (size_t)t * PS, r);
 #pragma unroll
     for (int b = 0; b < 9; ++b) d[b] = sD[9 * t + b];
 #pragma unroll
