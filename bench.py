@@ -14,7 +14,11 @@ one fixed problem); the reduced camera system is summed with ncclAllReduce insid
 
 `value` is device time (CUDA events on the library's own stream, max over ranks) with all inputs
 resident in HBM; `e2e` is the same step driven with HOST buffers through the C ABI (state upload +
-step download inside the timed region, wall clock, max over ranks).
+step download inside the timed region, wall clock, max over ranks). Also in the line: `roofline` (dominant stage against the
+measured FP64 / HBM peaks, ncu DRAM traffic, point stage against SURVEY 8(d)'s algorithmic bytes), `variants` (QRKIT next to
+QRCHOL), `parity_probe` (a sharded trial against the CPU oracle at this N, outside the timed regions), `clocks` (nvidia-smi samples
+inside the timed regions), `cpu_baseline` (N = 1: the oracle on the whole workload, all cores and single-threaded).
+`--impl reference`: the oracle on all host cores, whole workload, every step one complete LM iteration (rank 0 only).
 """
 from __future__ import annotations
 
