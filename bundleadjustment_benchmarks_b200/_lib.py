@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libba_b200.so")
 _SRC = [os.path.join(_HERE, "csrc", n) for n in
-        ("ba_gpu.cu", "ba_tile.cuh", "ba_model.cuh", "ba_dense.cuh", "ba_ldlt2.cuh", "ba_qr.cuh")] + \
+        ("ba_gpu.cu", "ba_tile.cuh", "ba_model.cuh", "ba_dense.cuh", "ba_ldlt2.cuh", "ba_split.cuh", "ba_qr.cuh")] + \
        [os.path.join(os.path.dirname(_HERE), "include", "ba_gpu.h")]
 
 # every symbol include/ba_gpu.h declares

@@ -530,7 +530,7 @@ __device__ __forceinline__ void frag_rc(int gt, int e, int& r, int& c) {
 template <class T> struct LdltProblem {
   BandMat<T> A; T* dvec; T* Wbuf; T* rhs; T* y; int* info; int np_fwd; int kb_bwd; int do_fwd; int do_bwd;
 };
-template <class T> struct LdltJob { LdltProblem<T> p[2]; T sign; };
+template <class T> struct LdltJob { LdltProblem<T> p[4]; T sign; };  // one problem per cluster of the launch
 
 // Kernel. Two teams of 4 warps per CTA:
 //   chain team (warps 0-3): per panel k stages the diagonal tile, warp 0 factors it (every CTA redundantly),

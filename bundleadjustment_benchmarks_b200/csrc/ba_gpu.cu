@@ -20,6 +20,7 @@
 #include "../../include/ba_gpu.h"
 #include "ba_dense.cuh"
 #include "ba_ldlt2.cuh"
+#include "ba_split.cuh"
 #include "ba_qr.cuh"
 #include "ba_tile.cuh"
 
@@ -292,6 +293,11 @@ struct Impl : ba_handle {
   int cluster_size = 16;  // non-portable size; falls back to 8 when 16 CTAs of this footprint cannot be co-scheduled
   bool solved_in_factor = false;
   int ldlt_roww = 6;  // row-tile warps per chain CTA of the cluster LDLT (BA_LDLT_ROWW=3|6)
+  bool ldlt_split = false;  // BA_LDLT_SPLIT=1: separator split, four elimination chains (ba_split.cuh)
+  struct SplitPart {        // one part of the separator split: index-reversed half, factors, spike
+    DevBuf<T> full, rev, dvec, dvec2, W, W2, y, y2, E;
+  } sp[2];
+  DevBuf<T> d_sep, d_sep_vec, d_sep_W;  // separator block (dense), [g | D | y], W
   bool ldlt_v2 = false; // BA_LDLT_V2=1: forward elimination of the two-sided scheme by the owner-computes kernel (ba_ldlt2.cuh; correct, not yet faster)
   DevBuf<double> d_partials, d_scal;
   DevBuf<long long> d_dbg;
@@ -525,6 +531,9 @@ struct Impl : ba_handle {
     if (const char* ra = std::getenv("BA_LDLT_ROWS_AFTER")) { if (atoi(ra) != 0) ldlt_roww |= 0x200; }
     if (const char* ts = std::getenv("BA_LDLT_TWOSIDED")) two_sided = atoi(ts) != 0;
     if (const char* v2 = std::getenv("BA_LDLT_V2")) ldlt_v2 = atoi(v2) != 0;
+    if (const char* v3 = std::getenv("BA_LDLT_SPLIT")) ldlt_split = atoi(v3) != 0;
+    CK(cudaFuncSetAttribute(k_spike, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpikeSmem)));
+    CK(cudaFuncSetAttribute(k_sep_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM));
     CK(cudaFuncSetAttribute(k_band_ldlt_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ldlt2Smem)));
     CK(cudaFuncSetAttribute(k_band_ldlt_fwd2, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     CK(cudaFuncSetAttribute(k_band_ldlt_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterSmem<T>)));
@@ -745,6 +754,117 @@ struct Impl : ba_handle {
   // factorisation of the reduced camera block in d_red (LDL^T or Householder QR of S)
   // solve_only: S is already factored (same handle, same band), only a new right-hand side sits in gvec(): forward
   // substitution with the existing factor (do_fwd = 2) instead of factorisation + folded forward substitution
+  // Separator split (ba_split.cuh): S = [part 0 | separator | part 1], four elimination chains side by side, spikes,
+  // separator Schur complement, then the backward passes in the opposite order. Returns false when the system is too
+  // small for it (the caller falls back to the two-sided scheme).
+  template <class L> int factor_reduced_split(bool solve_only, L&& launch, bool& done) {
+    done = false;
+    if constexpr (sizeof(T) == 8) {
+      const int fwd = solve_only ? 2 : 1;
+      const int bt = (kd + NB - 1) / NB;
+      int w = kd + 1; if (w & 1) ++w;
+      const int s0 = ((n - w) / 2) & ~1, p1 = s0 + w;
+      const int npart[2] = {s0, n - p1};
+      int q[2], r0[2], nm[2], nph[2], ntm[2], npE[2], ldE[2];
+      for (int p = 0; p < 2; ++p) {
+        q[p] = (npart[p] - (bt + 2) * NB) / (2 * NB);
+        if (q[p] < bt + 2) return BA_OK;
+        r0[p] = q[p] * NB; nm[p] = npart[p] - 2 * r0[p]; nph[p] = npart[p] - r0[p];
+        ntm[p] = (nm[p] + NB - 1) / NB; npE[p] = q[p] + ntm[p]; ldE[p] = npE[p] * NB;
+      }
+      if (bt > SPK_MAX_BT || (w - 1 + NB - 1) / NB > CL_MAX_BT) return BA_OK;
+      BandMat<T> A = band();
+      const size_t ldv = lds();
+      T* Xv[2]; T* gX[2]; T* yX[2]; T* Rv[2]; T* gr[2];
+      for (int p = 0; p < 2; ++p) {
+        SplitPart& P = sp[p];
+        const size_t revc = (size_t)nph[p] * (ldv + 1);
+        const int ntp = (npart[p] + NB - 1) / NB + 1, nth = (nph[p] + NB - 1) / NB + 1;
+        if (P.rev.n < revc + nph[p]) CK(P.rev.alloc(revc + nph[p]));
+        if (P.dvec.n < (size_t)npart[p] + 2 * NB) CK(P.dvec.alloc((size_t)npart[p] + 2 * NB));
+        if (P.dvec2.n < (size_t)nph[p] + 2 * NB) CK(P.dvec2.alloc((size_t)nph[p] + 2 * NB));
+        if (P.W.n < (size_t)ntp * NB * NB) CK(P.W.alloc((size_t)ntp * NB * NB));
+        if (P.W2.n < (size_t)nth * NB * NB) CK(P.W2.alloc((size_t)nth * NB * NB));
+        if (P.y2.n < (size_t)nph[p]) CK(P.y2.alloc(nph[p]));
+        if (P.E.n < (size_t)w * ldE[p]) CK(P.E.alloc((size_t)w * ldE[p]));
+        Rv[p] = P.rev.p + ldv; gr[p] = P.rev.p + revc;
+      }
+      {
+        const size_t fullc = (size_t)npart[0] * (ldv + 1);
+        if (sp[0].full.n < fullc + npart[0]) CK(sp[0].full.alloc(fullc + npart[0]));
+        if (sp[0].y.n < (size_t)npart[0]) CK(sp[0].y.alloc(npart[0]));
+        Xv[0] = sp[0].full.p + ldv; gX[0] = sp[0].full.p + fullc; yX[0] = sp[0].y.p;
+        Xv[1] = Sv() + (size_t)p1 * ldv + p1; gX[1] = gvec() + p1; yX[1] = d_dx_cam.p + p1;
+      }
+      const int kds = w - 1, ldw = pad_lds(kds), nts = (w + NB - 1) / NB;
+      const size_t sepc = (size_t)(w + 2 * NB) * (ldw + 1);
+      if (d_sep.n < sepc) { CK(d_sep.alloc(sepc)); CK(cudaMemsetAsync(d_sep.p, 0, sepc * sizeof(T), stream)); }
+      if (d_sep_vec.n < (size_t)3 * (w + 2 * NB)) CK(d_sep_vec.alloc((size_t)3 * (w + 2 * NB)));
+      if (d_sep_W.n < (size_t)(nts + 1) * NB * NB) CK(d_sep_W.alloc((size_t)(nts + 1) * NB * NB));
+      T* Sd = d_sep.p + ldw; T* gs = d_sep_vec.p; T* ds = gs + (w + 2 * NB); T* ys = ds + (w + 2 * NB);
+      const int ab = 4 * sm_count;
+      // part 0 as an index-reversed copy of its own (the separator then sits above row 0 of either part)
+      BandMat<T> A0{Sv(), ldv, npart[0], kd};
+      if (solve_only) k_rhs_reverse<T><<<64, 256, 0, stream>>>(gvec(), gX[0], npart[0], npart[0], npart[0]);
+      else k_band_reverse<T><<<ab, 256, 0, stream>>>(A0, gvec(), Xv[0], gX[0], npart[0], npart[0]);
+      BandMat<T> X[2], Ar[2], Am[2];
+      LdltJob<T> job = {}, mid = {};
+      job.sign = T(-1); mid.sign = T(-1);
+      for (int p = 0; p < 2; ++p) {
+        X[p] = BandMat<T>{Xv[p], ldv, npart[p], kd};
+        Ar[p] = BandMat<T>{Rv[p], ldv, nph[p], kd};
+        Am[p] = BandMat<T>{Xv[p] + (size_t)r0[p] * ldv + r0[p], ldv, nm[p], std::min(kd, nm[p] - 1)};
+        if (solve_only) k_rhs_reverse<T><<<64, 256, 0, stream>>>(gX[p], gr[p], npart[p], nph[p], r0[p]);
+        else k_band_reverse<T><<<ab / 2, 256, 0, stream>>>(X[p], gX[p], Rv[p], gr[p], nph[p], r0[p]);
+        job.p[2 * p] = LdltProblem<T>{X[p], sp[p].dvec.p, sp[p].W.p, gX[p], yX[p], d_info.p, q[p], 0, fwd, 0};
+        job.p[2 * p + 1] = LdltProblem<T>{Ar[p], sp[p].dvec2.p, sp[p].W2.p, gr[p], sp[p].y2.p, d_info.p, q[p], 0, fwd, 0};
+        mid.p[p] = LdltProblem<T>{Am[p], sp[p].dvec.p + r0[p], sp[p].W.p + (size_t)q[p] * NB * NB, gX[p] + r0[p], yX[p] + r0[p], d_info.p, ntm[p], 0, fwd, 0};
+      }
+      CK(launch(job, 4));
+      for (int p = 0; p < 2; ++p) {
+        if (solve_only) k_rhs_combine<T><<<8, 256, 0, stream>>>(gX[p], gr[p], npart[p], r0[p], nm[p]);
+        else k_band_combine<T><<<64, 256, 0, stream>>>(X[p], gX[p], Rv[p], gr[p], r0[p], nm[p]);
+      }
+      CK(launch(mid, 2));
+      const int ncolE[2] = {r0[0] + nm[0], r0[1] + nm[1]};
+      if (!solve_only) {
+        SpikeJob sj[2];
+        for (int p = 0; p < 2; ++p) {
+          k_spike_init<<<ab / 2, 256, 0, stream>>>(A, sp[p].E.p, ldE[p], w, (bt + 1) * NB, s0, p1, npart[p], p);
+          sj[p] = SpikeJob{BandMat<double>{Xv[p], ldv, ncolE[p], kd}, sp[p].dvec.p, sp[p].W.p, sp[p].E.p, ldE[p], 0, npE[p]};
+        }
+        const int nstrips = (w + SPK_STRIP - 1) / SPK_STRIP;
+        k_spike<<<2 * nstrips, SPK_THREADS, sizeof(SpikeSmem), stream>>>(sj[0], sj[1], w, d_dbg.p);
+        k_sep_syrk<<<nts * (nts + 1) / 2, 256, SYRK_SMEM, stream>>>(A, s0, w, Sd, ldw, SyrkSide{sp[0].E.p, ldE[0], sp[0].dvec.p, npE[0]},
+                                                                  SyrkSide{sp[1].E.p, ldE[1], sp[1].dvec.p, npE[1]});
+        launches += 4;
+      }
+      k_sep_rhs<<<w, 256, 0, stream>>>(gvec(), s0, w, gs, RhsSide{sp[0].E.p, ldE[0], sp[0].dvec.p, gX[0], ncolE[0]},
+                                                 RhsSide{sp[1].E.p, ldE[1], sp[1].dvec.p, gX[1], ncolE[1]});
+      LdltJob<T> sep = {};
+      sep.sign = T(-1);
+      sep.p[0] = LdltProblem<T>{BandMat<T>{Sd, (size_t)ldw, w, kds}, ds, d_sep_W.p, gs, ys, d_info.p, nts, nts, fwd, 1};
+      CK(launch(sep, 1));
+      for (int p = 0; p < 2; ++p) {
+        k_spike_correct<<<(ncolE[p] + 31) / 32, 256, 0, stream>>>(sp[p].E.p, ldE[p], ncolE[p], w, ys, -1.0, gX[p]);
+        mid.p[p].do_fwd = 0; mid.p[p].do_bwd = 1; mid.p[p].kb_bwd = ntm[p];
+      }
+      CK(launch(mid, 2));
+      for (int p = 0; p < 2; ++p) {
+        k_flip_copy<T><<<8, 256, 0, stream>>>(sp[p].y2.p, yX[p], npart[p], r0[p], nph[p]);
+        for (int c = 0; c < 2; ++c) { job.p[2 * p + c].do_fwd = 0; job.p[2 * p + c].do_bwd = 1; job.p[2 * p + c].kb_bwd = q[p]; }
+      }
+      CK(launch(job, 4));
+      for (int p = 0; p < 2; ++p) k_flip_copy<T><<<32, 256, 0, stream>>>(yX[p], sp[p].y2.p, npart[p], r0[p] + nm[p], npart[p]);
+      k_flip_copy<T><<<32, 256, 0, stream>>>(d_dx_cam.p, yX[0], npart[0], 0, npart[0]);
+      CK(cudaMemcpyAsync(d_dx_cam.p + s0, ys, (size_t)w * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+      launches += 14;
+      CK(cudaGetLastError());
+      done = true;
+    }
+    return BA_OK;
+  }
+
   int factor_reduced(bool solve_only = false) {
     if (variant == BA_QRCHOL || variant == BA_CHOLESKY || qr_csne) {
       if (!solve_only) CK(cudaMemsetAsync(d_info.p, 0, sizeof(int), stream));
@@ -780,7 +900,10 @@ struct Impl : ba_handle {
         };
         if (d_W.n < (size_t)nt * NB * NB) CK(d_W.alloc((size_t)nt * NB * NB));
         const int q = (n - (bt + 2) * NB) / (2 * NB);  // panels eliminated from either end by the two-sided scheme
-        if (!two_sided || q < bt + 2) {
+        bool split_done = false;
+        if (two_sided && ldlt_split && cluster_size == 16) { int rc = factor_reduced_split(solve_only, launch, split_done); if (rc) return rc; }
+        if (split_done) {
+        } else if (!two_sided || q < bt + 2) {
           LdltJob<T> job = {};
           job.sign = T(-1);
           job.p[0] = LdltProblem<T>{A, d_dvec.p, d_W.p, gvec(), d_dx_cam.p, d_info.p, nt, nt, fwd, 1};
