@@ -271,6 +271,9 @@ struct Impl : ba_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[9];
   cudaEvent_t tev[2] = {nullptr, nullptr};
+  cudaStream_t stream2 = nullptr;   // separator split: the spike kernel runs beside the next chain segment / the middle blocks
+  cudaEvent_t sev[10] = {};
+  int split_segments = 3;
   DevBuf<int> d_view, d_point, d_pt_start, d_tile_pt, d_info;
   DevBuf<int> d_slot, d_cam_start, d_blk_a, d_blk_b, d_blk_start, d_counter;  // static structure of the deterministic Schur gather
   DevBuf<int2> d_pairs;
@@ -315,6 +318,8 @@ struct Impl : ba_handle {
     if (h_stage) cudaFreeHost(h_stage);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : tev) if (e) cudaEventDestroy(e);
+    for (auto& e : sev) if (e) cudaEventDestroy(e);
+    if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -455,6 +460,8 @@ struct Impl : ba_handle {
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (auto& e : ev) CK(cudaEventCreate(&e));
+    CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    for (auto& e : sev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(d_view.alloc(K)); CK(d_point.alloc(K)); CK(d_pt_start.alloc(M + 1)); CK(d_tile_pt.alloc(4 * (size_t)ntiles + 4)); CK(d_huge_pt.alloc(nhuge + 1)); CK(d_info.alloc(1));
     CK(d_meas.alloc(2 * (size_t)K));
     CK(d_cams.alloc((size_t)N * CAM_STRIDE)); CK(d_cams_test.alloc((size_t)N * CAM_STRIDE));
@@ -532,6 +539,7 @@ struct Impl : ba_handle {
     if (const char* ts = std::getenv("BA_LDLT_TWOSIDED")) two_sided = atoi(ts) != 0;
     if (const char* v2 = std::getenv("BA_LDLT_V2")) ldlt_v2 = atoi(v2) != 0;
     if (const char* v3 = std::getenv("BA_LDLT_SPLIT")) ldlt_split = atoi(v3) != 0;
+    if (const char* v4 = std::getenv("BA_LDLT_SPLIT_SEGMENTS")) split_segments = std::max(1, std::min(4, atoi(v4)));
     CK(cudaFuncSetAttribute(k_spike, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpikeSmem)));
     CK(cudaFuncSetAttribute(k_sep_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM));
     CK(cudaFuncSetAttribute(k_band_ldlt_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ldlt2Smem)));
@@ -820,24 +828,57 @@ struct Impl : ba_handle {
         job.p[2 * p + 1] = LdltProblem<T>{Ar[p], sp[p].dvec2.p, sp[p].W2.p, gr[p], sp[p].y2.p, d_info.p, q[p], 0, fwd, 0};
         mid.p[p] = LdltProblem<T>{Am[p], sp[p].dvec.p + r0[p], sp[p].W.p + (size_t)q[p] * NB * NB, gX[p] + r0[p], yX[p] + r0[p], d_info.p, ntm[p], 0, fwd, 0};
       }
-      CK(launch(job, 4));
+      // The chains run in split_segments launches (a later segment is the same elimination on the view that starts at
+      // its first panel); the spike of a finished segment is formed on stream2 beside the next segment, the last one
+      // beside the middle blocks.
+      const int nseg = solve_only ? 1 : split_segments;
+      const int ncolE[2] = {r0[0] + nm[0], r0[1] + nm[1]};
+      const int nstrips = (w + SPK_STRIP - 1) / SPK_STRIP;
+      auto spike = [&](int seg0, int seg1, bool middle, cudaStream_t st) {
+        SpikeJob sj[2];
+        for (int p = 0; p < 2; ++p) {
+          const int kb = middle ? q[p] : (int)((long long)q[p] * seg0 / nseg), ke = middle ? npE[p] : (int)((long long)q[p] * seg1 / nseg);
+          sj[p] = SpikeJob{BandMat<double>{Xv[p], ldv, ncolE[p], kd}, sp[p].dvec.p, sp[p].W.p, sp[p].E.p, ldE[p], kb, ke};
+        }
+        k_spike<<<2 * nstrips, SPK_THREADS, sizeof(SpikeSmem), st>>>(sj[0], sj[1], w, d_dbg.p);
+        launches++;
+      };
+      if (!solve_only) {
+        for (int p = 0; p < 2; ++p) k_spike_init<<<ab / 2, 256, 0, stream>>>(A, sp[p].E.p, ldE[p], w, (bt + 1) * NB, s0, p1, npart[p], p);
+        launches += 2;
+      }
+      for (int sg = 0; sg < nseg; ++sg) {
+        LdltJob<T> seg = job;
+        for (int c = 0; c < 4; ++c) {
+          const int p = c / 2, a = (int)((long long)q[p] * sg / nseg), b = (int)((long long)q[p] * (sg + 1) / nseg);
+          LdltProblem<T>& P = seg.p[c];
+          P.A = BandMat<T>{P.A.v + (size_t)a * NB * (ldv + 1), ldv, P.A.n - a * NB, kd};
+          P.dvec += (size_t)a * NB; P.Wbuf += (size_t)a * NB * NB; P.rhs += (size_t)a * NB; P.y += (size_t)a * NB;
+          P.np_fwd = b - a;
+        }
+        CK(launch(seg, 4));
+        if (!solve_only) {
+          CK(cudaEventRecord(sev[sg], stream));
+          if (sg > 0) {               // spike of segment sg - 1 beside chain segment sg
+            CK(cudaStreamWaitEvent(stream2, sev[sg - 1], 0));
+            spike(sg - 1, sg, false, stream2);
+          }
+        }
+      }
       for (int p = 0; p < 2; ++p) {
         if (solve_only) k_rhs_combine<T><<<8, 256, 0, stream>>>(gX[p], gr[p], npart[p], r0[p], nm[p]);
         else k_band_combine<T><<<64, 256, 0, stream>>>(X[p], gX[p], Rv[p], gr[p], r0[p], nm[p]);
       }
       CK(launch(mid, 2));
-      const int ncolE[2] = {r0[0] + nm[0], r0[1] + nm[1]};
       if (!solve_only) {
-        SpikeJob sj[2];
-        for (int p = 0; p < 2; ++p) {
-          k_spike_init<<<ab / 2, 256, 0, stream>>>(A, sp[p].E.p, ldE[p], w, (bt + 1) * NB, s0, p1, npart[p], p);
-          sj[p] = SpikeJob{BandMat<double>{Xv[p], ldv, ncolE[p], kd}, sp[p].dvec.p, sp[p].W.p, sp[p].E.p, ldE[p], 0, npE[p]};
-        }
-        const int nstrips = (w + SPK_STRIP - 1) / SPK_STRIP;
-        k_spike<<<2 * nstrips, SPK_THREADS, sizeof(SpikeSmem), stream>>>(sj[0], sj[1], w, d_dbg.p);
+        CK(cudaStreamWaitEvent(stream2, sev[nseg - 1], 0));
+        spike(nseg - 1, nseg, false, stream2);      // beside the middle blocks
+        CK(cudaEventRecord(sev[8], stream2));
+        CK(cudaStreamWaitEvent(stream, sev[8], 0));
+        spike(0, 0, true, stream);                  // the middle panels
         k_sep_syrk<<<nts * (nts + 1) / 2, 256, SYRK_SMEM, stream>>>(A, s0, w, Sd, ldw, SyrkSide{sp[0].E.p, ldE[0], sp[0].dvec.p, npE[0]},
                                                                   SyrkSide{sp[1].E.p, ldE[1], sp[1].dvec.p, npE[1]});
-        launches += 4;
+        launches++;
       }
       k_sep_rhs<<<w, 256, 0, stream>>>(gvec(), s0, w, gs, RhsSide{sp[0].E.p, ldE[0], sp[0].dvec.p, gX[0], ncolE[0]},
                                                  RhsSide{sp[1].E.p, ldE[1], sp[1].dvec.p, gX[1], ncolE[1]});

@@ -158,6 +158,12 @@ __global__ void __launch_bounds__(SPK_THREADS, 1) k_spike(const SpikeJob j0, con
   for (int k = (kb > 0 ? kb - 1 : 0); k < ke; ++k) {
     const int k0 = k * NB;
     const bool finish = k >= kb;      // the first trip of a resumed walk only forms the far products of panel k_begin
+#ifdef BA_SPK_TICKS
+    long long tk[8]; tk[0] = clock64();
+#define SPT(i) tk[i] = clock64();
+#else
+#define SPT(i)
+#endif
     if (warp < SPK_PW) {
       double* pp = sm.part[warp];
 #pragma unroll
@@ -169,6 +175,7 @@ __global__ void __launch_bounds__(SPK_THREADS, 1) k_spike(const SpikeJob j0, con
           acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
         }
       spk_bar_arrive();
+      SPT(1)
       // far products of panel kn = k + 1: t = 1 .. min(kn, bt) - 1 with E_(kn-1-t) from the ring
       const int kn = k + 1, nprev = (kn < ke) ? min(kn, bt) : 0;
       const int ta = 1 + warp, tb2 = ta + SPK_PW;
@@ -178,8 +185,10 @@ __global__ void __launch_bounds__(SPK_THREADS, 1) k_spike(const SpikeJob j0, con
         spike_stage(buf, X, kn * NB, kpa * NB, 0, lane);
         spike_stage(buf, X, kn * NB, kpa * NB, 1, lane);
         spike_product(buf, sm.ring[kpa % R], X, J.dvec, kn, kpa, kpb, lane, acc);
+        SPT(2)
         if (kpb >= 0) spike_product(buf, sm.ring[kpb % R], X, J.dvec, kn, kpb, -1, lane, acc);
         cp_async_wait_all();
+        SPT(3)
       }
     } else {
       // finisher of rows 8 * fm .. of panel k
@@ -219,7 +228,9 @@ __global__ void __launch_bounds__(SPK_THREADS, 1) k_spike(const SpikeJob j0, con
             spike_mma<1>(es, bufn, dk, h, lr, lc, an);
           }
         }
+        SPT(1)
         spk_bar_sync();               // the product warps have written this panel's far partial sums
+        SPT(2)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
 #pragma unroll
@@ -232,6 +243,7 @@ __global__ void __launch_bounds__(SPK_THREADS, 1) k_spike(const SpikeJob j0, con
           }
         }
         __syncwarp();
+        SPT(3)
         double o[4][2], o2[4][2];     // two accumulator sets halve the dependent DMMA chain
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) o[ni][0] = o[ni][1] = o2[ni][0] = o2[ni][1] = 0.0;
@@ -252,12 +264,18 @@ __global__ void __launch_bounds__(SPK_THREADS, 1) k_spike(const SpikeJob j0, con
             if (rowok) Erow[k0 + c] = v;
           }
         }
+        SPT(4)
       } else {
         spk_bar_sync();
       }
     }
     __syncthreads();
+    SPT(5)
+#ifdef BA_SPK_TICKS
+    if (dbg && blockIdx.x == 5 && k == 60 && lane == 0) for (int i = 0; i < 6; ++i) dbg[128 + warp * 8 + i] = tk[i];
+#endif
   }
+#undef SPT
 }
 
 // Separator block: Sd (w x w, row stride ldw, lower triangle) = S[sep, sep] - sum_p E_p D_p E_p^T. One CTA per 32 x 32

@@ -8,8 +8,8 @@ s = solver.GpuSolver(prob, "QRCHOL")
 e, cn2, _ = s.linearize(); lam = 1e-12 * cn2
 for _ in range(3):
     s.compute(lam); out = s.solve_try(); s.reject()
-d = np.array(s.debug_counters_n(256))[128:208].reshape(10, 8)
+d = np.array(s.debug_counters_n(256))[128:216].reshape(11, 8)
 t0 = d[:, 0].min()
-for w in range(10):
+for w in range(11):
     print("warp", w, " ".join("%7d" % (d[w, i] - t0) for i in range(6)))
 s.close()
