@@ -814,7 +814,6 @@ struct Impl : ba_handle {
       // part 0 as an index-reversed copy of its own (the separator then sits above row 0 of either part)
       BandMat<T> A0{Sv(), ldv, npart[0], kd};
       if (solve_only) k_rhs_reverse<T><<<64, 256, 0, stream>>>(gvec(), gX[0], npart[0], npart[0], npart[0]);
-      else k_band_reverse<T><<<ab, 256, 0, stream>>>(A0, gvec(), Xv[0], gX[0], npart[0], npart[0]);
       BandMat<T> X[2], Ar[2], Am[2];
       LdltJob<T> job = {}, mid = {};
       job.sign = T(-1); mid.sign = T(-1);
@@ -823,10 +822,20 @@ struct Impl : ba_handle {
         Ar[p] = BandMat<T>{Rv[p], ldv, nph[p], kd};
         Am[p] = BandMat<T>{Xv[p] + (size_t)r0[p] * ldv + r0[p], ldv, nm[p], std::min(kd, nm[p] - 1)};
         if (solve_only) k_rhs_reverse<T><<<64, 256, 0, stream>>>(gX[p], gr[p], npart[p], nph[p], r0[p]);
-        else k_band_reverse<T><<<ab / 2, 256, 0, stream>>>(X[p], gX[p], Rv[p], gr[p], nph[p], r0[p]);
         job.p[2 * p] = LdltProblem<T>{X[p], sp[p].dvec.p, sp[p].W.p, gX[p], yX[p], d_info.p, q[p], 0, fwd, 0};
         job.p[2 * p + 1] = LdltProblem<T>{Ar[p], sp[p].dvec2.p, sp[p].W2.p, gr[p], sp[p].y2.p, d_info.p, q[p], 0, fwd, 0};
         mid.p[p] = LdltProblem<T>{Am[p], sp[p].dvec.p + r0[p], sp[p].W.p + (size_t)q[p] * NB * NB, gX[p] + r0[p], yX[p] + r0[p], d_info.p, ntm[p], 0, fwd, 0};
+      }
+      if (!solve_only) {
+        // the reversed half of (index-reversed) part 0 is the top of part 0 as it stands; all three copies in one launch
+        RevJob<T> rj0{A0, gvec(), Xv[0], gX[0], npart[0], npart[0], 1};
+        RevJob<T> rj1{A0, gvec(), Rv[0], gr[0], nph[0], r0[0], 0};
+        RevJob<T> rj2{X[1], gX[1], Rv[1], gr[1], nph[1], r0[1], 1};
+        k_band_reverse3<T><<<dim3(2 * sm_count, 3), 256, 0, stream>>>(rj0, rj1, rj2);
+        CK(cudaEventRecord(sev[9], stream));
+        CK(cudaStreamWaitEvent(stream2, sev[9], 0));
+        for (int p = 0; p < 2; ++p) k_spike_init<<<ab / 2, 256, 0, stream2>>>(A, sp[p].E.p, ldE[p], w, (bt + 1) * NB, s0, p1, npart[p], p);
+        launches += 3;
       }
       // The chains run in split_segments launches (a later segment is the same elimination on the view that starts at
       // its first panel); the spike of a finished segment is formed on stream2 beside the next segment, the last one
@@ -841,12 +850,11 @@ struct Impl : ba_handle {
           sj[p] = SpikeJob{BandMat<double>{Xv[p], ldv, ncolE[p], kd}, sp[p].dvec.p, sp[p].W.p, sp[p].E.p, ldE[p], kb, ke};
         }
         k_spike<<<2 * nstrips, SPK_THREADS, sizeof(SpikeSmem), st>>>(sj[0], sj[1], w, d_dbg.p);
-        launches++;
-      };
-      if (!solve_only) {
-        for (int p = 0; p < 2; ++p) k_spike_init<<<ab / 2, 256, 0, stream>>>(A, sp[p].E.p, ldE[p], w, (bt + 1) * NB, s0, p1, npart[p], p);
+        // the separator block receives the Schur complement of the same panels right away
+        k_sep_syrk<<<nts * (nts + 1) / 2, 256, SYRK_SMEM, st>>>(A, s0, w, Sd, ldw, SyrkSide{sp[0].E.p, ldE[0], sp[0].dvec.p, sj[0].k_begin, sj[0].k_end},
+                                                              SyrkSide{sp[1].E.p, ldE[1], sp[1].dvec.p, sj[1].k_begin, sj[1].k_end}, (!middle && seg0 == 0) ? 1 : 0);
         launches += 2;
-      }
+      };
       for (int sg = 0; sg < nseg; ++sg) {
         LdltJob<T> seg = job;
         for (int c = 0; c < 4; ++c) {
@@ -876,9 +884,6 @@ struct Impl : ba_handle {
         CK(cudaEventRecord(sev[8], stream2));
         CK(cudaStreamWaitEvent(stream, sev[8], 0));
         spike(0, 0, true, stream);                  // the middle panels
-        k_sep_syrk<<<nts * (nts + 1) / 2, 256, SYRK_SMEM, stream>>>(A, s0, w, Sd, ldw, SyrkSide{sp[0].E.p, ldE[0], sp[0].dvec.p, npE[0]},
-                                                                  SyrkSide{sp[1].E.p, ldE[1], sp[1].dvec.p, npE[1]});
-        launches++;
       }
       k_sep_rhs<<<w, 256, 0, stream>>>(gvec(), s0, w, gs, RhsSide{sp[0].E.p, ldE[0], sp[0].dvec.p, gX[0], ncolE[0]},
                                                  RhsSide{sp[1].E.p, ldE[1], sp[1].dvec.p, gX[1], ncolE[1]});
@@ -886,10 +891,8 @@ struct Impl : ba_handle {
       sep.sign = T(-1);
       sep.p[0] = LdltProblem<T>{BandMat<T>{Sd, (size_t)ldw, w, kds}, ds, d_sep_W.p, gs, ys, d_info.p, nts, nts, fwd, 1};
       CK(launch(sep, 1));
-      for (int p = 0; p < 2; ++p) {
-        k_spike_correct<<<(ncolE[p] + 31) / 32, 256, 0, stream>>>(sp[p].E.p, ldE[p], ncolE[p], w, ys, -1.0, gX[p]);
-        mid.p[p].do_fwd = 0; mid.p[p].do_bwd = 1; mid.p[p].kb_bwd = ntm[p];
-      }
+      k_spike_correct<<<dim3((std::max(ncolE[0], ncolE[1]) + 31) / 32, 2), 256, 0, stream>>>(CorrSide{sp[0].E.p, ldE[0], ncolE[0], gX[0]}, CorrSide{sp[1].E.p, ldE[1], ncolE[1], gX[1]}, w, ys, -1.0);
+      for (int p = 0; p < 2; ++p) { mid.p[p].do_fwd = 0; mid.p[p].do_bwd = 1; mid.p[p].kb_bwd = ntm[p]; }
       CK(launch(mid, 2));
       for (int p = 0; p < 2; ++p) {
         k_flip_copy<T><<<8, 256, 0, stream>>>(sp[p].y2.p, yX[p], npart[p], r0[p], nph[p]);

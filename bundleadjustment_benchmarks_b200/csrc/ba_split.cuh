@@ -278,10 +278,11 @@ __global__ void __launch_bounds__(SPK_THREADS, 1) k_spike(const SpikeJob j0, con
 #undef SPT
 }
 
-// Separator block: Sd (w x w, row stride ldw, lower triangle) = S[sep, sep] - sum_p E_p D_p E_p^T. One CTA per 32 x 32
-// tile (ta >= tb); its 8 warps split the panels of both spikes and are summed in a fixed order.
-struct SyrkSide { const double* E; int ldE; const double* dvec; int npanels; };
-__global__ void __launch_bounds__(256) k_sep_syrk(BandMat<double> A, int s0, int w, double* __restrict__ Sd, int ldw, SyrkSide e0, SyrkSide e1) {
+// Separator block: Sd (w x w, row stride ldw, lower triangle) = S[sep, sep] - sum_p E_p D_p E_p^T, accumulated over panel
+// ranges (init = 1 on the first range, which starts from S[sep, sep]). One CTA per 32 x 32 tile (ta >= tb); its 8 warps
+// split the panels of both spikes and are summed in a fixed order.
+struct SyrkSide { const double* E; int ldE; const double* dvec; int kb, ke; };   // panels [kb, ke) of the spike
+__global__ void __launch_bounds__(256) k_sep_syrk(BandMat<double> A, int s0, int w, double* __restrict__ Sd, int ldw, SyrkSide e0, SyrkSide e1, int init) {
   extern __shared__ __align__(16) unsigned char syrk_raw[];
   double (*red)[NB][NB + 1] = reinterpret_cast<double (*)[NB][NB + 1]>(syrk_raw);
   const int nts = (w + NB - 1) / NB;
@@ -295,10 +296,10 @@ __global__ void __launch_bounds__(256) k_sep_syrk(BandMat<double> A, int s0, int
   for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-  const int ntot = e0.npanels + e1.npanels;
+  const int n0 = e0.ke - e0.kb, ntot = n0 + e1.ke - e1.kb;
   for (int pidx = warp; pidx < ntot; pidx += 8) {
-    const SyrkSide& S = (pidx < e0.npanels) ? e0 : e1;
-    const int kp = (pidx < e0.npanels) ? pidx : pidx - e0.npanels;
+    const SyrkSide& S = (pidx < n0) ? e0 : e1;
+    const int kp = (pidx < n0) ? e0.kb + pidx : e1.kb + pidx - n0;
     const double* Ea = S.E + (size_t)kp * NB;
     double dk[8];
 #pragma unroll
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(256) k_sep_syrk(BandMat<double> A, int s0, int
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int r = idx >> 5, c = idx & 31, gi = ta * NB + r, gj = tb * NB + c;
     if (gi >= w || gj > gi) continue;
-    double v = (gi - gj <= A.kd) ? A.v[(size_t)(s0 + gi) * A.lds + (s0 + gj)] : 0.0;
+    double v = init ? ((gi - gj <= A.kd) ? A.v[(size_t)(s0 + gi) * A.lds + (s0 + gj)] : 0.0) : Sd[(size_t)gi * ldw + gj];
 #pragma unroll
     for (int q = 0; q < 8; ++q) v -= red[q][r][c];
     Sd[(size_t)gi * ldw + gj] = v;
@@ -374,26 +375,48 @@ __global__ void __launch_bounds__(256) k_sep_rhs(const double* __restrict__ g, i
 
 // w_p(c) -= sum_s E_p(s, c) * (sign * ysep(s)): the separator's solution enters the parts' backward passes. One CTA per
 // 32 columns, warp g sums the rows s = g mod 8; fixed order.
-__global__ void __launch_bounds__(256) k_spike_correct(const double* __restrict__ E, int ldE, int ncol, int w, const double* __restrict__ ysep, double sign, double* __restrict__ wv) {
+struct CorrSide { const double* E; int ldE; int ncol; double* wv; };
+__global__ void __launch_bounds__(256) k_spike_correct(CorrSide c0, CorrSide c1, int w, const double* __restrict__ ysep, double sign) {
   __shared__ double red[8][32];
+  const CorrSide& S = blockIdx.y ? c1 : c0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = blockIdx.x * 32 + lane;
+  if (blockIdx.x * 32 >= S.ncol) return;
   double a0 = 0.0, a1 = 0.0;
-  if (c < ncol) {
+  if (c < S.ncol) {
     int s = warp;
     for (; s + 8 < w; s += 16) {
-      a0 += E[(size_t)s * ldE + c] * ysep[s];
-      a1 += E[(size_t)(s + 8) * ldE + c] * ysep[s + 8];
+      a0 += S.E[(size_t)s * S.ldE + c] * ysep[s];
+      a1 += S.E[(size_t)(s + 8) * S.ldE + c] * ysep[s + 8];
     }
-    if (s < w) a0 += E[(size_t)s * ldE + c] * ysep[s];
+    if (s < w) a0 += S.E[(size_t)s * S.ldE + c] * ysep[s];
   }
   red[warp][lane] = a0 + a1;
   __syncthreads();
-  if (warp == 0 && c < ncol) {
+  if (warp == 0 && c < S.ncol) {
     double t = 0.0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) t += red[q][lane];
-    wv[c] -= sign * t;
+    S.wv[c] -= sign * t;
   }
+}
+
+// The three index-reversed copies of the split in one launch (k_band_reverse for each job; they are independent: the
+// reversed half of the index-reversed part 0 is the top of part 0 as it stands).
+template <class T> struct RevJob { BandMat<T> A; const T* g; T* Rv; T* gr; int np, mrow0, flip; };   // flip = 0: plain copy of the top np rows
+template <class T>
+__global__ void k_band_reverse3(RevJob<T> j0, RevJob<T> j1, RevJob<T> j2) {
+  const RevJob<T>& J = blockIdx.y == 0 ? j0 : (blockIdx.y == 1 ? j1 : j2);
+  const int n = J.A.n, kd = J.A.kd, np = J.np, mrow0 = J.mrow0;
+  const size_t lds = J.A.lds, total = (size_t)np * (kd + 1), stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int ip = (int)(idx / (kd + 1)), d = (int)(idx - (size_t)ip * (kd + 1)), jp = ip - d;
+    if (jp < 0) continue;
+    T v = T(0);
+    if (!(ip >= mrow0 && jp >= mrow0)) v = J.flip ? J.A.v[(size_t)(n - 1 - jp) * lds + (n - 1 - ip)] : J.A.v[(size_t)ip * lds + jp];
+    J.Rv[(size_t)ip * lds + jp] = v;
+  }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)np; i += stride)
+    J.gr[i] = ((int)i < mrow0) ? (J.flip ? J.g[n - 1 - i] : J.g[i]) : T(0);
 }
 
 }  // namespace ba
