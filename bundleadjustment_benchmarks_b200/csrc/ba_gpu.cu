@@ -296,7 +296,7 @@ struct Impl : ba_handle {
   int cluster_size = 16;  // non-portable size; falls back to 8 when 16 CTAs of this footprint cannot be co-scheduled
   bool solved_in_factor = false;
   int ldlt_roww = 6;  // row-tile warps per chain CTA of the cluster LDLT (BA_LDLT_ROWW=3|6)
-  bool ldlt_split = false;  // BA_LDLT_SPLIT=1: separator split, four elimination chains (ba_split.cuh)
+  int ldlt_split = 1;       // separator split, four elimination chains (ba_split.cuh): BA_LDLT_SPLIT=0 off, 1 when the chains are long enough to pay for it, 2 whenever possible
   struct SplitPart {        // one part of the separator split: index-reversed half, factors, spike
     DevBuf<T> full, rev, dvec, dvec2, W, W2, y, y2, E;
   } sp[2];
@@ -538,7 +538,7 @@ struct Impl : ba_handle {
     if (const char* ra = std::getenv("BA_LDLT_ROWS_AFTER")) { if (atoi(ra) != 0) ldlt_roww |= 0x200; }
     if (const char* ts = std::getenv("BA_LDLT_TWOSIDED")) two_sided = atoi(ts) != 0;
     if (const char* v2 = std::getenv("BA_LDLT_V2")) ldlt_v2 = atoi(v2) != 0;
-    if (const char* v3 = std::getenv("BA_LDLT_SPLIT")) ldlt_split = atoi(v3) != 0;
+    if (const char* v3 = std::getenv("BA_LDLT_SPLIT")) ldlt_split = atoi(v3);
     if (const char* v4 = std::getenv("BA_LDLT_SPLIT_SEGMENTS")) split_segments = std::max(1, std::min(4, atoi(v4)));
     CK(cudaFuncSetAttribute(k_spike, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpikeSmem)));
     CK(cudaFuncSetAttribute(k_sep_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM));
@@ -776,7 +776,8 @@ struct Impl : ba_handle {
       int q[2], r0[2], nm[2], nph[2], ntm[2], npE[2], ldE[2];
       for (int p = 0; p < 2; ++p) {
         q[p] = (npart[p] - (bt + 2) * NB) / (2 * NB);
-        if (q[p] < bt + 2) return BA_OK;
+        // shorter chains do not pay for the extra stages (middle blocks, spike, separator: about 60 panel times at bt = 18)
+        if (q[p] < bt + 2 || (ldlt_split < 2 && q[p] < 2 * bt + 8)) return BA_OK;
         r0[p] = q[p] * NB; nm[p] = npart[p] - 2 * r0[p]; nph[p] = npart[p] - r0[p];
         ntm[p] = (nm[p] + NB - 1) / NB; npE[p] = q[p] + ntm[p]; ldE[p] = npE[p] * NB;
       }

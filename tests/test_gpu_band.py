@@ -26,14 +26,17 @@ def band_spd(n, kd, seed):
     return A, rng.standard_normal(n)
 
 
-def _solve(variant, precision, force_grid):
+def _solve(variant, precision, force_grid, env=None):
     prob = bal.synthetic(4, 40, seed=3)
+    env = dict(env or {})
     if force_grid:
-        os.environ["BA_FORCE_GRID_LDLT"] = "1"
+        env["BA_FORCE_GRID_LDLT"] = "1"
+    os.environ.update(env)
     try:
         s = solver.GpuSolver(prob, variant, precision)
     finally:
-        os.environ.pop("BA_FORCE_GRID_LDLT", None)
+        for k in env:
+            os.environ.pop(k, None)
     return s
 
 
@@ -57,19 +60,36 @@ def test_band_solve_two_sided(n, kd):
     Ragged sizes (n, n - 2*32*q not multiples of 32), compared with numpy and with the one-sided kernel."""
     A, g = band_spd(n, kd, 300 + n)
     ref = np.linalg.solve(A, g)
-    s2 = _solve("QRCHOL", "f64", False)
+    s2 = _solve("QRCHOL", "f64", False, {"BA_LDLT_SPLIT": "0"})
     y2 = s2.debug_band_solve(A, g, kd)
     s2.close()
-    os.environ["BA_LDLT_TWOSIDED"] = "0"
-    try:
-        s1 = _solve("QRCHOL", "f64", False)
-    finally:
-        os.environ.pop("BA_LDLT_TWOSIDED", None)
+    s1 = _solve("QRCHOL", "f64", False, {"BA_LDLT_TWOSIDED": "0"})
     y1 = s1.debug_band_solve(A, g, kd)
     s1.close()
     assert np.linalg.norm(y2 - ref) / np.linalg.norm(ref) < 1e-12
     assert np.linalg.norm(y1 - ref) / np.linalg.norm(ref) < 1e-12
     assert np.linalg.norm(y2 - y1) / np.linalg.norm(ref) < 1e-12
+
+
+@pytest.mark.parametrize("n,kd,segments", [(1990, 31, 3), (3001, 100, 1), (2500, 257, 4), (2433, 64, 2), (5001, 548, 3), (6000, 576, 3)])
+def test_band_solve_separator_split(n, kd, segments):
+    """Separator split (ba_split.cuh): S = [part 0 | separator | part 1], four elimination chains, the spike of either part
+    (k_spike), the separator's Schur complement (k_sep_syrk) and the corrected backward passes, forced on (BA_LDLT_SPLIT=2)
+    for 1..18 row tiles per panel, ragged part / middle-block sizes and 1..4 chain segments; against numpy and against the
+    two-sided kernel. The same factor then serves a second right-hand side in solve-only mode through the QR variants'
+    refinement (test_solve_with_existing_factor)."""
+    A, g = band_spd(n, kd, 300 + n)
+    ref = np.linalg.solve(A, g)
+    s4 = _solve("QRCHOL", "f64", False, {"BA_LDLT_SPLIT": "2", "BA_LDLT_SPLIT_SEGMENTS": str(segments)})
+    y4 = s4.debug_band_solve(A, g, kd)
+    y4b = s4.debug_band_solve(A, g, kd)
+    s4.close()
+    s2 = _solve("QRCHOL", "f64", False, {"BA_LDLT_SPLIT": "0"})
+    y2 = s2.debug_band_solve(A, g, kd)
+    s2.close()
+    nr = np.linalg.norm(ref)
+    assert np.linalg.norm(y4 - ref) / nr < 1e-12 and np.linalg.norm(y4 - y2) / nr < 1e-12
+    assert np.array_equal(y4, y4b)          # fixed summation orders: bit-reproducible
 
 
 @pytest.mark.parametrize("n,kd", [(1990, 31), (3001, 100), (2500, 257), (4100, 548), (5000, 576)])
@@ -79,14 +99,10 @@ def test_band_solve_owner_computes_forward(n, kd):
     kernel, for 1..18 row tiles per panel (kd = 31 .. 576), band edges cutting through tiles, ragged n."""
     A, g = band_spd(n, kd, 300 + n)
     ref = np.linalg.solve(A, g)
-    os.environ["BA_LDLT_V2"] = "1"
-    try:
-        s2 = _solve("QRCHOL", "f64", False)
-    finally:
-        os.environ.pop("BA_LDLT_V2", None)
+    s2 = _solve("QRCHOL", "f64", False, {"BA_LDLT_V2": "1", "BA_LDLT_SPLIT": "0"})
     y2 = s2.debug_band_solve(A, g, kd)
     s2.close()
-    s1 = _solve("QRCHOL", "f64", False)
+    s1 = _solve("QRCHOL", "f64", False, {"BA_LDLT_SPLIT": "0"})
     y1 = s1.debug_band_solve(A, g, kd)
     s1.close()
     nr = np.linalg.norm(ref)
