@@ -169,14 +169,14 @@ __global__ void __launch_bounds__(128) k_colnorm_cam(const int* __restrict__ cam
 }
 
 // deterministic final reduction: block b sums partials[b*count .. (b+1)*count) -> out[b]
-__global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ partials, int count, double* __restrict__ out) {
-  __shared__ double s[256];
+__global__ void __launch_bounds__(1024) k_reduce(const double* __restrict__ partials, int count, double* __restrict__ out) {
+  __shared__ double s[1024];
   const double* p = partials + (size_t)blockIdx.x * count;
   double acc = 0.0;
-  for (int i = threadIdx.x; i < count; i += 256) acc += p[i];
+  for (int i = threadIdx.x; i < count; i += blockDim.x) acc += p[i];
   s[threadIdx.x] = acc;
   __syncthreads();
-  for (int off = 128; off > 0; off >>= 1) { if ((int)threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off]; __syncthreads(); }
+  for (int off = blockDim.x / 2; off > 0; off >>= 1) { if ((int)threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off]; __syncthreads(); }
   if (threadIdx.x == 0) out[blockIdx.x] = s[0];
 }
 
@@ -191,14 +191,19 @@ __global__ void __launch_bounds__(256) k_max(const T* __restrict__ v, int n, dou
   if (threadIdx.x == 0) out[0] = s[0];
 }
 
-// cams_test = update(cams, dx_cam) (update_params, BAFunctor.h:311-333) and |dx_cam|^2. One CTA.
+// cams_test = update(cams, dx_cam) (update_params, BAFunctor.h:311-333), |dx_cam|^2 and dx_cam . gJ. One camera per thread,
+// 128 per CTA; the CTA that arrives last sums the per-CTA partial sums in index order (deterministic).
+constexpr int CAMUP_THREADS = 128;
 template <class T>
-__global__ void __launch_bounds__(1024) k_cam_update(int N, const T* __restrict__ cams, const T* __restrict__ dx_cam, const T* __restrict__ gJ,
-                                                     T* __restrict__ cams_test, double* __restrict__ out_norm2, double* __restrict__ out_dot) {
-  __shared__ double s[1024];
-  __shared__ double s2[1024];
+__global__ void __launch_bounds__(CAMUP_THREADS) k_cam_update(int N, const T* __restrict__ cams, const T* __restrict__ dx_cam, const T* __restrict__ gJ,
+                                                              T* __restrict__ cams_test, double* __restrict__ out_norm2, double* __restrict__ out_dot,
+                                                              double* __restrict__ part, unsigned int* __restrict__ counter) {
+  __shared__ double s[CAMUP_THREADS];
+  __shared__ double s2[CAMUP_THREADS];
+  __shared__ bool last;
   double acc = 0.0, acc2 = 0.0;
-  for (int c = threadIdx.x; c < N; c += 1024) {
+  const int c = blockIdx.x * CAMUP_THREADS + threadIdx.x;
+  if (c < N) {
     const T* ci = cams + (size_t)c * CAM_STRIDE;
     T* co = cams_test + (size_t)c * CAM_STRIDE;
     T d[9];
@@ -215,8 +220,20 @@ __global__ void __launch_bounds__(1024) k_cam_update(int N, const T* __restrict_
   }
   s[threadIdx.x] = acc; s2[threadIdx.x] = acc2;
   __syncthreads();
-  for (int off = 512; off > 0; off >>= 1) { if ((int)threadIdx.x < off) { s[threadIdx.x] += s[threadIdx.x + off]; s2[threadIdx.x] += s2[threadIdx.x + off]; } __syncthreads(); }
-  if (threadIdx.x == 0) { out_norm2[0] = s[0]; out_dot[0] = s2[0]; }
+  for (int off = CAMUP_THREADS / 2; off > 0; off >>= 1) { if ((int)threadIdx.x < off) { s[threadIdx.x] += s[threadIdx.x + off]; s2[threadIdx.x] += s2[threadIdx.x + off]; } __syncthreads(); }
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = s[0]; part[2 * blockIdx.x + 1] = s2[0];
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double a = 0.0, a2 = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) { a += __ldcg(part + 2 * b); a2 += __ldcg(part + 2 * b + 1); }
+    out_norm2[0] = a; out_dot[0] = a2;
+    *counter = 0u;
+  }
 }
 
 template <class T> struct DevBuf {
@@ -271,6 +288,8 @@ struct Impl : ba_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[9];
   cudaEvent_t tev[2] = {nullptr, nullptr};
+  DevBuf<double> d_camup; DevBuf<unsigned int> d_camup_cnt;   // k_cam_update: per-CTA partial sums, arrival counter
+  int camup_blocks() const { return (N + CAMUP_THREADS - 1) / CAMUP_THREADS; }
   cudaStream_t stream2 = nullptr;   // separator split: the spike kernel runs beside the next chain segment / the middle blocks
   cudaEvent_t sev[10] = {};
   int split_segments = 3;
@@ -468,6 +487,7 @@ struct Impl : ba_handle {
     CK(d_X.alloc(3 * (size_t)M)); CK(d_X_test.alloc(3 * (size_t)M));
     CK(d_dx_pt.alloc(3 * (size_t)M)); CK(d_dx_cam.alloc(9 * (size_t)N));
     const size_t npart = std::max<size_t>(3 * (size_t)(ntiles + nhuge), (size_t)(K + 255) / 256);
+    CK(d_camup.alloc(2 * (size_t)camup_blocks())); CK(d_camup_cnt.alloc(1)); CK(cudaMemset(d_camup_cnt.p, 0, sizeof(unsigned int)));
     CK(d_partials.alloc(npart)); CK(d_scal.alloc(16)); CK(d_dbg.alloc(256)); CK(cudaMemset(d_dbg.p, 0, 256 * sizeof(long long)));
     CK(cudaMallocHost(&h_scal, 16 * sizeof(double)));
     CK(cudaMemcpyAsync(d_view.p, view, K * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -645,7 +665,7 @@ struct Impl : ba_handle {
   int energy_pass(int slot) {
     const int nb = (K + 255) / 256;
     k_obs<T, 0><<<nb, 256, 0, stream>>>(K, d_view.p, d_point.p, d_meas.p, d_cams.p, d_X.p, tau2, M, d_partials.p, nullptr, nullptr);
-    k_reduce<<<1, 256, 0, stream>>>(d_partials.p, nb, d_scal.p + slot);
+    k_reduce<<<1, 1024, 0, stream>>>(d_partials.p, nb, d_scal.p + slot);
     launches += 2;
     CK(cudaGetLastError());
     return allreduce_scal(slot, 1);
@@ -681,7 +701,7 @@ struct Impl : ba_handle {
       const size_t np = 3 * (size_t)M + 9 * (size_t)N;
       if (d_tmp.n < np) CK(d_tmp.alloc(np));
       k_obs<T, 0><<<nb, 256, 0, stream>>>(K, d_view.p, d_point.p, d_meas.p, d_cams.p, d_X.p, tau2, M, d_partials.p, nullptr, nullptr);
-      k_reduce<<<1, 256, 0, stream>>>(d_partials.p, nb, d_scal.p + 0);
+      k_reduce<<<1, 1024, 0, stream>>>(d_partials.p, nb, d_scal.p + 0);
       k_colnorm_pt<T><<<(M + 255) / 256, 256, 0, stream>>>(M, d_pt_start.p, d_view.p, d_meas.p, d_cams.p, d_X.p, tau2, d_tmp.p);
       k_colnorm_cam<T><<<N, 128, 0, stream>>>(d_cam_start.p, d_obs_of_slot.p, d_point.p, d_meas.p, d_cams.p, d_X.p, tau2, d_tmp.p + 3 * (size_t)M);
       launches += 4;
@@ -1111,7 +1131,7 @@ struct Impl : ba_handle {
     CK(cudaGetLastError());
     if (qr_csne) { int rc = csne_refine(lamT); if (rc) return rc; }
     mark(5);
-    k_cam_update<T><<<1, 1024, 0, stream>>>(N, d_cams.p, d_dx_cam.p, gJvec(), d_cams_test.p, d_scal.p + 4, d_scal.p + 6);
+    k_cam_update<T><<<camup_blocks(), CAMUP_THREADS, 0, stream>>>(N, d_cams.p, d_dx_cam.p, gJvec(), d_cams_test.p, d_scal.p + 4, d_scal.p + 6, d_camup.p, d_camup_cnt.p);
     launches++;
     mark(6);
     const int ntot = ntiles + nhuge;
@@ -1125,7 +1145,7 @@ struct Impl : ba_handle {
 
     CK(cudaGetLastError());
     mark(7);
-    k_reduce<<<3, 256, 0, stream>>>(d_partials.p, ntot, d_scal.p + 1);
+    k_reduce<<<3, 1024, 0, stream>>>(d_partials.p, ntot, d_scal.p + 1);
     launches++;
     int rc = allreduce_scal(1, 3);
     if (rc) return rc;

@@ -9,7 +9,7 @@ from test_gpu_band import band_spd
 
 small = bal.synthetic(4, 40, seed=3)
 def make(split):
-    if split: os.environ["BA_LDLT_SPLIT"] = "1"
+    os.environ["BA_LDLT_SPLIT"] = "2" if split else "0"
     s = solver.GpuSolver(small, "QRCHOL")
     os.environ.pop("BA_LDLT_SPLIT", None)
     return s
@@ -30,7 +30,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "noperf": sys.exit(0)
 prob = bal.load_named("synthetic-5m")
 ref = None
 for split in (False, True):
-    if split: os.environ["BA_LDLT_SPLIT"] = "1"
+    os.environ["BA_LDLT_SPLIT"] = "1" if split else "0"
     s = solver.GpuSolver(prob, "QRCHOL")
     os.environ.pop("BA_LDLT_SPLIT", None)
     e, cn2, _ = s.linearize(); lam = 1e-12 * cn2
