@@ -14,7 +14,8 @@ one fixed problem); the reduced camera system is summed with ncclAllReduce insid
 
 `value` is device time (CUDA events on the library's own stream, max over ranks) with all inputs
 resident in HBM; `e2e` is the same step driven with HOST buffers through the C ABI (state upload +
-step download inside the timed region, wall clock, max over ranks). Also in the line: `roofline` (dominant stage against the
+step download inside the timed region, wall clock, max over ranks; one ba_step_streamed call per step, which pipelines the
+copies against the point stage and returns bit-identical results). Also in the line: `roofline` (dominant stage against the
 measured FP64 / HBM peaks, ncu DRAM traffic, point stage against SURVEY 8(d)'s algorithmic bytes), `variants` (QRKIT next to
 QRCHOL), `parity_probe` (a sharded trial against the CPU oracle at this N, outside the timed regions), `clocks` (nvidia-smi samples
 inside the timed regions), `cpu_baseline` (N = 1: the oracle on the whole workload, all cores and single-threaded).
@@ -300,10 +301,11 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 10))
 
     def e2e_step():
-        s.set_state(R, T, f, k1, k2, X)
-        out = step()
-        s.dx_into(dx_h)
-        return out
+        # one call: state upload + energy + compute + solve_try + step download, copies pipelined against the point stage
+        # (ba_step_streamed; bit-identical to set_state / linearize / compute / solve_try / get_dx called one by one)
+        out = s.step_streamed(R, T, f, k1, k2, X, lam, dx_h)
+        s.reject()
+        return out[1:]
 
     for _ in range(2):
         e2e_step()

@@ -250,6 +250,7 @@ struct ba_handle {
   virtual ~ba_handle() {}
   virtual int set_state(const double*, const double*, const double*, const double*, const double*, const double*) = 0;
   virtual int get_state(double*, double*, double*, double*, double*, double*) = 0;
+  virtual int step_streamed(const double*, const double*, const double*, const double*, const double*, const double*, double, double*, double*, double*, double*, double*) = 0;
   virtual int eval(double*) = 0;
   virtual int linearize(double*, double*, double*) = 0;
   virtual int compute(double) = 0;
@@ -293,6 +294,14 @@ struct Impl : ba_handle {
   cudaStream_t stream2 = nullptr;   // separator split: the spike kernel runs beside the next chain segment / the middle blocks
   cudaEvent_t sev[10] = {};
   int split_segments = 3;
+  // ba_step_streamed: the point coordinates are uploaded in chunks on stream2 while the point-factor kernel already works on
+  // the chunks that have arrived, and dx is downloaded in chunks behind the back-substitution kernel
+  static constexpr int SX_MAX = 16;
+  int sx_chunks = 8, sx_n = 0, sx_unit[SX_MAX + 1] = {};
+  bool sx_active = false;
+  double* dx_sink = nullptr;
+  cudaEvent_t xev[SX_MAX + 2] = {}, bev[SX_MAX + 2] = {};
+  std::vector<int> h_unit_last_pt, h_tile_first;
   DevBuf<int> d_view, d_point, d_pt_start, d_tile_pt, d_info;
   DevBuf<int> d_slot, d_cam_start, d_blk_a, d_blk_b, d_blk_start, d_counter;  // static structure of the deterministic Schur gather
   DevBuf<int2> d_pairs;
@@ -338,6 +347,8 @@ struct Impl : ba_handle {
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : tev) if (e) cudaEventDestroy(e);
     for (auto& e : sev) if (e) cudaEventDestroy(e);
+    for (auto& e : xev) if (e) cudaEventDestroy(e);
+    for (auto& e : bev) if (e) cudaEventDestroy(e);
     if (stream2) cudaStreamDestroy(stream2);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -419,6 +430,10 @@ struct Impl : ba_handle {
       j = j1;
     }
     nunits = (int)unit_pt.size() / 2; nbig = (int)big_pt.size() / 2;
+    h_unit_last_pt.resize(nunits);
+    for (int u = 0; u < nunits; ++u) h_unit_last_pt[u] = point[unit_pt[2 * u] + unit_pt[2 * u + 1] - 1];
+    h_tile_first.resize(ntiles);
+    for (int t = 0; t < ntiles; ++t) h_tile_first[t] = tile_pt[4 * (size_t)t];
     std::vector<int> long_pt;
     for (int j = 0; j < M; ++j) if (pt_start[j + 1] - pt_start[j] > 32) long_pt.push_back(j);
     nlong = (int)long_pt.size();
@@ -481,6 +496,9 @@ struct Impl : ba_handle {
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     for (auto& e : sev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : xev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : bev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (const char* sc = std::getenv("BA_STREAM_CHUNKS")) sx_chunks = std::max(1, std::min(SX_MAX, atoi(sc)));
     CK(d_view.alloc(K)); CK(d_point.alloc(K)); CK(d_pt_start.alloc(M + 1)); CK(d_tile_pt.alloc(4 * (size_t)ntiles + 4)); CK(d_huge_pt.alloc(nhuge + 1)); CK(d_info.alloc(1));
     CK(d_meas.alloc(2 * (size_t)K));
     CK(d_cams.alloc((size_t)N * CAM_STRIDE)); CK(d_cams_test.alloc((size_t)N * CAM_STRIDE));
@@ -636,6 +654,60 @@ struct Impl : ba_handle {
     return BA_OK;
   }
 
+  // One LM trial from host state to host step in one call: set_state + linearize (energy only) + compute + solve_try +
+  // get_dx, with the copies pipelined against the point stage (see sx_* above). Same results, bit for bit, as the
+  // separate calls. Host buffers should be page-locked for the copies to overlap; they must stay valid until the call returns.
+  int step_streamed(const double* R, const double* Tt, const double* f, const double* k1, const double* k2, const double* X, double lam,
+                    double* dx, double* energy, double* dx_norm, double* rho_den, double* energy_test) override {
+    CK(cudaSetDevice(device));
+    if (sizeof(T) != sizeof(double) || two_stage) {
+      int rc = set_state(R, Tt, f, k1, k2, X);
+      if (!rc) rc = linearize(energy, nullptr, nullptr);
+      if (!rc) rc = compute(lam);
+      if (!rc) rc = solve_try(dx_norm, rho_den, energy_test);
+      if (!rc && dx) rc = get_dx(dx);
+      return rc;
+    }
+    const size_t nc = (size_t)N * CAM_STRIDE;
+    { int rc = stage_buf(nc); if (rc) return rc; }
+    T* c = h_stage;
+    for (int i = 0; i < N; ++i) {
+      T* o = c + (size_t)i * CAM_STRIDE;
+      for (int b = 0; b < 9; ++b) o[b] = (T)R[9 * (size_t)i + b];
+      for (int b = 0; b < 3; ++b) o[9 + b] = (T)Tt[3 * (size_t)i + b];
+      o[12] = (T)f[i]; o[13] = (T)k1[i]; o[14] = (T)k2[i]; o[15] = T(0);
+    }
+    CK(cudaEventRecord(xev[SX_MAX], stream));          // whatever still reads the old state finishes first
+    CK(cudaStreamWaitEvent(stream2, xev[SX_MAX], 0));
+    CK(cudaMemcpyAsync(d_cams.p, c, nc * sizeof(T), cudaMemcpyHostToDevice, stream2));
+    sx_n = std::max(1, std::min(sx_chunks, std::max(nunits, 1)));
+    int p0 = 0;
+    sx_unit[0] = 0;
+    for (int ch = 0; ch < sx_n; ++ch) {
+      const int u1 = (int)((long long)nunits * (ch + 1) / sx_n);
+      const int p1 = (ch == sx_n - 1) ? M : (u1 > 0 ? std::max(p0, h_unit_last_pt[u1 - 1] + 1) : p0);
+      if (p1 > p0)
+        CK(cudaMemcpyAsync(reinterpret_cast<double*>(d_X.p) + 3 * (size_t)p0, X + 3 * (size_t)p0, 3 * (size_t)(p1 - p0) * sizeof(double), cudaMemcpyHostToDevice, stream2));
+      CK(cudaEventRecord(xev[ch], stream2));
+      sx_unit[ch + 1] = u1;
+      p0 = p1;
+    }
+    sx_active = true;
+    computed = tried = linearized = false; stage1_valid = false;
+    int rc = compute(lam);
+    sx_active = false;
+    if (rc) return rc;
+    rc = energy_pass(0);                                // all of X has arrived: the last chunk's units waited for it
+    if (rc) return rc;
+    linearized = true;
+    dx_sink = dx;
+    rc = solve_try(dx_norm, rho_den, energy_test);
+    dx_sink = nullptr;
+    if (rc) return rc;
+    if (energy) *energy = h_scal[0];
+    return BA_OK;
+  }
+
   int get_state(double* R, double* Tt, double* f, double* k1, double* k2, double* X) override {
     CK(cudaSetDevice(device));
     const size_t nc = (size_t)N * CAM_STRIDE, nx = 3 * (size_t)M;
@@ -742,7 +814,20 @@ struct Impl : ba_handle {
       k_moreqr_stage2<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, point_factor_warp_smem_bytes<T>(), stream>>>(lamT, nunits, d_unit_pt.p, d_seg.p, d_slot.p, d_point.p,
                                                                                                                  d_J.p, d_Pt0.p, d_P.p, d_D.p, d_Pt.p);
       launches++;
+    } else if (nunits && sx_active) {
+      // streamed state upload: the units of a chunk start as soon as the points they read have arrived
+      constexpr int UPB = TILE / 32;
+      for (int c = 0; c < sx_n; ++c) {
+        CK(cudaStreamWaitEvent(stream, xev[c], 0));
+        const int u0 = sx_unit[c], nu = sx_unit[c + 1] - u0;
+        if (nu > 0) {
+          k_point_factor_warp<T><<<(nu + UPB - 1) / UPB, TILE, point_factor_warp_smem_bytes<T>(), stream>>>(tile_args(lamT), nu, d_unit_pt.p + 2 * (size_t)u0, d_seg.p, d_slot.p, d_P.p, d_D.p, d_Pt.p);
+          launches++;
+        }
+      }
+      sx_active = false;
     } else if (nunits) { k_point_factor_warp<T><<<(nunits + TILE / 32 - 1) / (TILE / 32), TILE, point_factor_warp_smem_bytes<T>(), stream>>>(tile_args(lamT), nunits, d_unit_pt.p, d_seg.p, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++; }
+    if (sx_active) { for (int c = 0; c < sx_n; ++c) CK(cudaStreamWaitEvent(stream, xev[c], 0)); sx_active = false; }
     if (nbig) {
       TileArgs<T> ab = tile_args(lamT); ab.tile_pt = d_big_pt.p;
       k_point_factor<T><<<nbig, TILE, sizeof(TileSmem<T>), stream>>>(ab, 2, d_slot.p, d_P.p, d_D.p, d_Pt.p); launches++;
@@ -1135,13 +1220,37 @@ struct Impl : ba_handle {
     launches++;
     mark(6);
     const int ntot = ntiles + nhuge;
-    if (ntiles)
-      k_backsub_eval<T><<<ntiles, TILE, backsub_smem_bytes<T>(), stream>>>(tile_args(lamT), d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
-                                                      d_partials.p, ntot);
     if (nhuge)
       k_backsub_big<T><<<nhuge, BIG_THREADS, 0, stream>>>(tile_args(lamT), d_huge_pt.p, d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
                                                           d_partials.p, ntiles, ntot);
-    launches += (ntiles ? 1 : 0) + (nhuge ? 1 : 0);
+    if (ntiles && dx_sink && sizeof(T) == sizeof(double)) {
+      // streamed download: the step of the points of a chunk of tiles goes to the host while the next chunk is computed
+      const int C = std::max(1, std::min(sx_chunks, ntiles));
+      CK(cudaEventRecord(bev[SX_MAX], stream));
+      CK(cudaStreamWaitEvent(stream2, bev[SX_MAX], 0));
+      CK(cudaMemcpyAsync(dx_sink + 3 * (size_t)M, d_dx_cam.p, 9 * (size_t)N * sizeof(T), cudaMemcpyDeviceToHost, stream2));
+      int p0 = 0;
+      for (int c = 0; c < C; ++c) {
+        const int t0 = (int)((long long)ntiles * c / C), t1 = (int)((long long)ntiles * (c + 1) / C);
+        if (t1 <= t0) continue;
+        TileArgs<T> ta = tile_args(lamT); ta.tile_pt = d_tile_pt.p + 4 * (size_t)t0;
+        k_backsub_eval<T><<<t1 - t0, TILE, backsub_smem_bytes<T>(), stream>>>(ta, d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
+                                                                            d_partials.p + t0, ntot);
+        launches++;
+        const int p1 = (t1 == ntiles) ? M : h_tile_first[t1];
+        CK(cudaEventRecord(bev[c], stream));
+        CK(cudaStreamWaitEvent(stream2, bev[c], 0));
+        CK(cudaMemcpyAsync(dx_sink + 3 * (size_t)p0, d_dx_pt.p + 3 * (size_t)p0, 3 * (size_t)(p1 - p0) * sizeof(T), cudaMemcpyDeviceToHost, stream2));
+        p0 = p1;
+      }
+      CK(cudaEventRecord(bev[SX_MAX + 1], stream2));
+      CK(cudaStreamWaitEvent(stream, bev[SX_MAX + 1], 0));
+    } else if (ntiles) {
+      k_backsub_eval<T><<<ntiles, TILE, backsub_smem_bytes<T>(), stream>>>(tile_args(lamT), d_P.p, d_Pt.p, d_dx_cam.p, d_cams_test.p, d_dx_pt.p, d_X_test.p,
+                                                      d_partials.p, ntot);
+      launches++;
+    }
+    launches += (nhuge ? 1 : 0);
 
     CK(cudaGetLastError());
     mark(7);
@@ -1366,6 +1475,10 @@ int ba_solve_try(ba_handle* h, double* dx_norm, double* rho_den, double* energy_
 int ba_accept(ba_handle* h) { H_CHECK; return h->accept(); }
 int ba_reject(ba_handle* h) { H_CHECK; return h->reject(); }
 int ba_get_dx(ba_handle* h, double* dx) { H_CHECK; return h->get_dx(dx); }
+int ba_step_streamed(ba_handle* h, const double* R, const double* T, const double* f, const double* k1, const double* k2, const double* X, double lambda,
+                     double* dx, double* energy, double* dx_norm, double* rho_den, double* energy_test) {
+  H_CHECK; return h->step_streamed(R, T, f, k1, k2, X, lambda, dx, energy, dx_norm, rho_den, energy_test);
+}
 int ba_get_residuals(ba_handle* h, double* r) { H_CHECK; return h->get_residuals(r); }
 int ba_get_reduced_system(ba_handle* h, double* S, double* g) { H_CHECK; return h->get_reduced(S, g); }
 int ba_keep_reduced_system(ba_handle* h, int enable) { H_CHECK; h->keep_reduced = enable != 0; return BA_OK; }

@@ -140,6 +140,18 @@ class GpuSolver:
         self._ck(self._L.ba_get_dx(self._h, _dp(v)))
         return v
 
+    def step_streamed(self, R, T, f, k1, k2, X, lam, dx_out=None):
+        """One trial from host state to host step (ba_step_streamed): upload, energy, compute(lam), solve_try and the step
+        download in one call with the copies pipelined against the point stage. Pass contiguous (ideally pinned) float64
+        arrays; returns (energy, |dx|, rho denominator, test energy) and fills dx_out (3M+9N) when given."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (R, T, f, k1, k2, X)]
+        if dx_out is not None:
+            assert dx_out.dtype == np.float64 and dx_out.size == self.n and dx_out.flags["C_CONTIGUOUS"]
+        e, a, b, c = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        self._ck(self._L.ba_step_streamed(self._h, *[_dp(x) for x in arrs], float(lam), _dp(dx_out) if dx_out is not None else None,
+                                          C.byref(e), C.byref(a), C.byref(b), C.byref(c)))
+        return e.value, a.value, b.value, c.value
+
     def dx_into(self, out):
         """Step download into a caller-owned (ideally pinned) float64 buffer of 3M+9N entries."""
         assert out.dtype == np.float64 and out.size == self.n and out.flags["C_CONTIGUOUS"]

@@ -95,6 +95,16 @@ int ba_solve_try(ba_handle* h, double* dx_norm, double* rho_denominator, double*
 int ba_numeric_status(ba_handle* h, int* info);
 int ba_set_strict_numeric(ba_handle* h, int enable);
 
+/* One LM trial from host state to host step in ONE call, for a caller that keeps x on the host the way the reference's LM loop does
+ * (x handed to functor(x) / functor.df(x) and to solver.compute / solve on every trial, QRChol.h:257-372): ba_set_state +
+ * ba_linearize (energy only) + ba_compute(lambda) + ba_solve_try + ba_get_dx, with the host<->device copies pipelined against the
+ * point stage: the point coordinates go up in chunks while the point-factor kernel works on the chunks that have arrived, and dx
+ * comes down in chunks behind the back-substitution kernel. Results are bit-identical to the separate calls. dx: 3M+9N doubles
+ * (may be NULL: no download). The host buffers should be page-locked (otherwise the copies do not overlap) and must stay valid
+ * until the call returns; it blocks like ba_solve_try. Float build / MOREQR two-stage: runs the separate calls in sequence. */
+int ba_step_streamed(ba_handle* h, const double* R, const double* T, const double* f, const double* k1, const double* k2, const double* X,
+                     double lambda, double* dx, double* energy, double* dx_norm, double* rho_den, double* energy_test);
+
 /* ≙ x = xTest (QRChol.h:428) / discarding xTest on a rejected trial. */
 int ba_accept(ba_handle* h);
 int ba_reject(ba_handle* h);

@@ -444,3 +444,43 @@ def test_float_build_all_variants(small, p21, p39, variant):
                 # cond(S) eps_f32 >> 1: a non-finite trial is a rejection (QRChol.h:374); a finite one must be a real step
                 assert (not np.isfinite(et)) or (e - et) > 0.5 * (e - eto), (prob.name, variant, et, eto)
         s.close()
+
+
+@pytest.mark.parametrize("variant,precision", [("QRCHOL", "f64"), ("QRKIT", "f64"), ("CHOLESKY", "f64"), ("MOREQR", "f64"), ("QRCHOL", "f32")])
+def test_streamed_step_equals_separate_calls(variant, precision):
+    """ba_step_streamed (chunked state upload beside the point-factor kernel, chunked step download behind the back-substitution
+    kernel) returns bit for bit what ba_set_state + ba_linearize + ba_compute + ba_solve_try + ba_get_dx return, for several chunk
+    counts, on a problem with long tracks (tiles, big and huge points) and on a banded synthetic one; MOREQR two-stage and the
+    float build take the sequential fallback inside the call."""
+    import os
+    import torch
+    for prob in (bal.load_named("problem-39-18060"), bal.synthetic(120, 30000, window=12, seed=21)):
+        for chunks in ("1", "3", "8"):
+            os.environ["BA_STREAM_CHUNKS"] = chunks
+            try:
+                s = solver.GpuSolver(prob, variant, precision)
+            finally:
+                os.environ.pop("BA_STREAM_CHUNKS", None)
+            e, cn2, cn = s.linearize()
+            lam = 1e-6 * cn if variant == "MOREQR" else 1e-9 * cn2
+            state = [np.ascontiguousarray(a, dtype=np.float64) for a in s.get_state()]
+            # perturbed state, so that the upload matters
+            rng = np.random.default_rng(5)
+            state[5] = state[5] + 1e-3 * rng.standard_normal(state[5].shape)
+            state[1] = state[1] + 1e-4 * rng.standard_normal(state[1].shape)
+            pinned = [torch.from_numpy(a.copy()).pin_memory() for a in state]
+            host = [t.numpy() for t in pinned]
+            s.set_state(*host)
+            e1, _, _ = s.linearize(colnorms=False)
+            s.compute(lam)
+            dxn1, rho1, et1 = s.solve_try()
+            dx1 = s.dx().copy()
+            s.reject()
+            dx_t = torch.empty(s.n, dtype=torch.float64).pin_memory()
+            dx2 = dx_t.numpy()
+            dx2[:] = np.nan
+            e2, dxn2, rho2, et2 = s.step_streamed(*host, lam, dx2)
+            s.reject()
+            assert (e1, dxn1, rho1, et1) == (e2, dxn2, rho2, et2), (prob.name, chunks)
+            assert np.array_equal(dx1, dx2), (prob.name, chunks)
+            s.close()
