@@ -180,6 +180,44 @@ __global__ void __launch_bounds__(1024) k_reduce(const double* __restrict__ part
   if (threadIdx.x == 0) out[blockIdx.x] = s[0];
 }
 
+// Reporting (Utils::showErrorStatistics / showObjective, src/Utils.h:15-68) as a reduction over the observations at the
+// device-resident state: per-block partial sums of the reprojection error avg_f |p - m|, of the inliers' errors, of the
+// inlier count and of the "true objective" psi(tau^2, avg_f^2 |p - m|) (the norm, not its square: quirk Q7 of the survey).
+template <class T>
+__global__ void __launch_bounds__(256) k_stats(int K, const int* __restrict__ view, const int* __restrict__ point, const T* __restrict__ meas,
+                                               const T* __restrict__ cams, const T* __restrict__ X, T avg_f, T thr, double* __restrict__ partials, int nb) {
+  __shared__ double sred[4][8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  if (i < K) {
+    const int cidx = __ldg(view + i), pj = __ldg(point + i);
+    Cam<T> c; load_cam<T>(cams, cidx, c);
+    const T X0 = __ldg(X + 3 * (size_t)pj), X1 = __ldg(X + 3 * (size_t)pj + 1), X2 = __ldg(X + 3 * (size_t)pj + 2);
+    const T xx = c.R[0] * X0 + c.R[1] * X1 + c.R[2] * X2 + c.t[0];
+    const T yy = c.R[3] * X0 + c.R[4] * X1 + c.R[5] * X2 + c.t[1];
+    const T zz = c.R[6] * X0 + c.R[7] * X1 + c.R[8] * X2 + c.t[2];
+    const T xu0 = xx / zz, xu1 = yy / zz, r2u = xu0 * xu0 + xu1 * xu1, kr = T(1) + c.k1 * r2u + c.k2 * r2u * r2u;
+    const T r0 = c.f * (kr * xu0) - __ldg(meas + 2 * (size_t)i), r1 = c.f * (kr * xu1) - __ldg(meas + 2 * (size_t)i + 1);
+    const T en = tsqrt(r0 * r0 + r1 * r1), e = avg_f * en;
+    v[0] = (double)e;
+    if (e <= thr) { v[1] = (double)e; v[2] = 1.0; }
+    const T tau2 = thr * thr, q2 = avg_f * avg_f * en, q4 = q2 * q2;
+    v[3] = (double)((q2 < tau2) ? q2 * (T(3.0) - T(3.0) * q2 / tau2 + q4 / (tau2 * tau2)) / T(6.0) : tau2 / T(6.0));
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], off);
+    if ((threadIdx.x & 31) == 0) sred[q][threadIdx.x >> 5] = v[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sred[threadIdx.x][w];
+    partials[(size_t)threadIdx.x * nb + blockIdx.x] = t;
+  }
+}
+
 template <class T>
 __global__ void __launch_bounds__(256) k_max(const T* __restrict__ v, int n, double* __restrict__ out) {
   __shared__ double s[256];
@@ -259,6 +297,7 @@ struct ba_handle {
   virtual int reject() = 0;
   virtual int get_dx(double*) = 0;
   virtual int get_residuals(double*) = 0;
+  virtual int error_statistics(double, double, double*) = 0;
   virtual int get_reduced(double*, double*) = 0;
   virtual int get_jacobian(double*, double*) = 0;
   virtual int comm_init(int, int, const void*) = 0;
@@ -329,6 +368,7 @@ struct Impl : ba_handle {
     DevBuf<T> full, rev, dvec, dvec2, W, W2, y, y2, E;
   } sp[2];
   DevBuf<T> d_sep, d_sep_vec, d_sep_W;  // separator block (dense), [g | D | y], W
+  int sep_w = -1;
   bool ldlt_v2 = false; // BA_LDLT_V2=1: forward elimination of the two-sided scheme by the owner-computes kernel (ba_ldlt2.cuh; correct, not yet faster)
   DevBuf<double> d_partials, d_scal;
   DevBuf<long long> d_dbg;
@@ -912,7 +952,8 @@ struct Impl : ba_handle {
       }
       const int kds = w - 1, ldw = pad_lds(kds), nts = (w + NB - 1) / NB;
       const size_t sepc = (size_t)(w + 2 * NB) * (ldw + 1);
-      if (d_sep.n < sepc) { CK(d_sep.alloc(sepc)); CK(cudaMemsetAsync(d_sep.p, 0, sepc * sizeof(T), stream)); }
+      if (d_sep.n < sepc) CK(d_sep.alloc(sepc));
+      if (sep_w != w) { CK(cudaMemsetAsync(d_sep.p, 0, d_sep.n * sizeof(T), stream)); sep_w = w; }   // nothing stale outside the lower triangle
       if (d_sep_vec.n < (size_t)3 * (w + 2 * NB)) CK(d_sep_vec.alloc((size_t)3 * (w + 2 * NB)));
       if (d_sep_W.n < (size_t)(nts + 1) * NB * NB) CK(d_sep_W.alloc((size_t)(nts + 1) * NB * NB));
       T* Sd = d_sep.p + ldw; T* gs = d_sep_vec.p; T* ds = gs + (w + 2 * NB); T* ys = ds + (w + 2 * NB);
@@ -1315,6 +1356,22 @@ struct Impl : ba_handle {
     return d2h(d_dx_cam.p, dx + 3 * (size_t)M, 9 * (size_t)N);
   }
 
+  int error_statistics(double avg_f, double thr, double* out4) override {
+    CK(cudaSetDevice(device));
+    const int nb = (K + 255) / 256;
+    if (d_partials.n < 4 * (size_t)nb) { CK(cudaStreamSynchronize(stream)); CK(d_partials.alloc(4 * (size_t)nb)); }
+    k_stats<T><<<nb, 256, 0, stream>>>(K, d_view.p, d_point.p, d_meas.p, d_cams.p, d_X.p, (T)avg_f, (T)thr, d_partials.p, nb);
+    k_reduce<<<4, 1024, 0, stream>>>(d_partials.p, nb, d_scal.p + 10);
+    launches += 2;
+    CK(cudaGetLastError());
+    int rc = allreduce_scal(10, 4);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_scal + 10, d_scal.p + 10, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int q = 0; q < 4; ++q) out4[q] = h_scal[10 + q];
+    return BA_OK;
+  }
+
   int get_residuals(double* r) override {
     CK(cudaSetDevice(device));
     if (d_tmp.n < 2 * (size_t)K) CK(d_tmp.alloc(2 * (size_t)K));
@@ -1479,6 +1536,7 @@ int ba_step_streamed(ba_handle* h, const double* R, const double* T, const doubl
                      double* dx, double* energy, double* dx_norm, double* rho_den, double* energy_test) {
   H_CHECK; return h->step_streamed(R, T, f, k1, k2, X, lambda, dx, energy, dx_norm, rho_den, energy_test);
 }
+int ba_error_statistics(ba_handle* h, double avg_focal_length, double inlier_threshold, double* sums) { H_CHECK; if (!sums) return BA_ERR_ARG; return h->error_statistics(avg_focal_length, inlier_threshold, sums); }
 int ba_get_residuals(ba_handle* h, double* r) { H_CHECK; return h->get_residuals(r); }
 int ba_get_reduced_system(ba_handle* h, double* S, double* g) { H_CHECK; return h->get_reduced(S, g); }
 int ba_keep_reduced_system(ba_handle* h, int enable) { H_CHECK; h->keep_reduced = enable != 0; return BA_OK; }

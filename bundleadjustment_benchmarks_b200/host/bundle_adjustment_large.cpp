@@ -43,41 +43,17 @@ inline void createRotationMatrixRodrigues(const double om[3], double R[9]) {
 }  // namespace Math
 
 namespace Utils {
-// src/Utils.h:10-68 — reporting only (runs twice per process, on the host)
-inline double psi(double tau2, double r2) { const double r4 = r2 * r2, tau4 = tau2 * tau2; return (r2 < tau2) ? r2 * (3.0 - 3.0 * r2 / tau2 + r4 / tau4) / 6.0 : tau2 / 6.0; }
-inline void project(const OptimizationFunctor::InputType& x, int i, int j, double p[2]) {
-  const double* R = &x.R[9 * (size_t)i]; const double* T = &x.T[3 * (size_t)i]; const double* X = &x.X[3 * (size_t)j];
-  double XX[3];
-  for (int r = 0; r < 3; ++r) XX[r] = R[3 * r] * X[0] + R[3 * r + 1] * X[1] + R[3 * r + 2] * X[2] + T[r];
-  const double xu = XX[0] / XX[2], yu = XX[1] / XX[2], r2 = xu * xu + yu * yu, kr = 1 + x.k1[i] * r2 + x.k2[i] * r2 * r2;
-  p[0] = x.f[i] * kr * xu; p[1] = x.f[i] * kr * yu;
-}
-inline double showErrorStatistics(double avg_f, double inlierThreshold, const OptimizationFunctor::InputType& x, const std::vector<double>& meas,
-                                  const std::vector<int>& view, const std::vector<int>& point) {
-  const int K = (int)view.size();
-  int nInliers = 0; double mean = 0, inl = 0;
-  for (int k = 0; k < K; ++k) {
-    double p[2]; project(x, view[k], point[k], p);
-    const double e = avg_f * std::hypot(p[0] - meas[2 * (size_t)k], p[1] - meas[2 * (size_t)k + 1]);
-    mean += e;
-    if (e <= inlierThreshold) { ++nInliers; inl += e; }
-  }
-  std::cout << "Mean reprojection error: " << mean / K << std::endl;
-  std::cout << "Inlier mean reprojection error: " << inl / nInliers << " (" << nInliers << " / " << K << " inliers)" << std::endl;
+// src/Utils.h:15-68 as ONE reduction on the GPU at the functor's device-resident state (ba_error_statistics): the two calls
+// print exactly the reference's three lines
+inline double showErrorStatisticsAndObjective(OptimizationFunctor& functor, double avg_f, double inlierThreshold) {
+  double s[4];
+  ba_check(ba_error_statistics(functor.gpu, avg_f, inlierThreshold, s));
+  const long K = functor.numMeasurements;
+  const long nInliers = (long)s[2];
+  std::cout << "Mean reprojection error: " << s[0] / K << std::endl;
+  std::cout << "Inlier mean reprojection error: " << s[1] / nInliers << " (" << nInliers << " / " << K << " inliers)" << std::endl;
+  std::cout << "True objective: " << s[3] << std::endl;
   return double(nInliers) / K;
-}
-inline double showObjective(double avg_f, double inlierThreshold, const OptimizationFunctor::InputType& x, const std::vector<double>& meas,
-                            const std::vector<int>& view, const std::vector<int>& point) {
-  const int K = (int)view.size();
-  const double tau2 = inlierThreshold * inlierThreshold, f2 = avg_f * avg_f;
-  double obj = 0;
-  for (int k = 0; k < K; ++k) {
-    double p[2]; project(x, view[k], point[k], p);
-    const double r2 = f2 * std::hypot(p[0] - meas[2 * (size_t)k], p[1] - meas[2 * (size_t)k + 1]);  // norm, not squared (quirk Q7)
-    obj += psi(tau2, r2);
-  }
-  std::cout << "True objective: " << obj << std::endl;
-  return obj;
 }
 }  // namespace Utils
 
@@ -156,12 +132,11 @@ int main(int argc, char* argv[]) {
     }
   }
 
-  Utils::showErrorStatistics(avg_focal_length, INLIER_THRESHOLD, params, measurements, correspondingView, correspondingPoint);
-  Utils::showObjective(avg_focal_length, INLIER_THRESHOLD, params, measurements, correspondingView, correspondingPoint);
-
   const int device = std::getenv("BA_DEVICE") ? std::atoi(std::getenv("BA_DEVICE")) : 0;
   try {
     OptimizationFunctor functor(M, N, measurements, correspondingView, correspondingPoint, INLIER_THRESHOLD, device);
+    functor.upload(params);
+    Utils::showErrorStatisticsAndObjective(functor, avg_focal_length, INLIER_THRESHOLD);   // :130-131
     BacktrackLevMarqGPU<OptimizationFunctor, true> lm(functor);
     if (std::getenv("BA_MAX_ITERS")) lm.lmParams().maxIter = std::atoi(std::getenv("BA_MAX_ITERS"));
     const auto begin = std::chrono::steady_clock::now();
@@ -174,12 +149,11 @@ int main(int argc, char* argv[]) {
       o << "iter,accepted,energy,energy_test,rho,lambda_used,lambda_next,dx_norm,elapsed_s\n";
       for (const auto& t : lm.log()) o << t.iter << ',' << t.accepted << ',' << t.energy << ',' << t.energyTest << ',' << t.rho << ',' << t.lambdaUsed << ',' << t.lambdaNext << ',' << t.dxNorm << ',' << t.elapsed << '\n';
     }
+    Utils::showErrorStatisticsAndObjective(functor, avg_focal_length, INLIER_THRESHOLD);   // :170-171, at the final state on the device
   } catch (const std::exception& e) {
     std::cerr << "error: " << e.what() << std::endl;
     return 3;
   }
 
-  Utils::showErrorStatistics(avg_focal_length, INLIER_THRESHOLD, params, measurements, correspondingView, correspondingPoint);
-  Utils::showObjective(avg_focal_length, INLIER_THRESHOLD, params, measurements, correspondingView, correspondingPoint);
   return ReturnCodes::Success;
 }

@@ -152,6 +152,13 @@ class GpuSolver:
                                           C.byref(e), C.byref(a), C.byref(b), C.byref(c)))
         return e.value, a.value, b.value, c.value
 
+    def error_statistics(self, avg_focal_length: float, inlier_threshold: float):
+        """Utils::showErrorStatistics / showObjective at the device state: (mean reprojection error, inlier mean error,
+        number of inliers, true objective)."""
+        out = np.zeros(4)
+        self._ck(self._L.ba_error_statistics(self._h, float(avg_focal_length), float(inlier_threshold), _dp(out)))
+        return out[0] / self.K, (out[1] / out[2] if out[2] > 0 else float("nan")), int(out[2]), out[3]
+
     def dx_into(self, out):
         """Step download into a caller-owned (ideally pinned) float64 buffer of 3M+9N entries."""
         assert out.dtype == np.float64 and out.size == self.n and out.flags["C_CONTIGUOUS"]

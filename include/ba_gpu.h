@@ -109,6 +109,13 @@ int ba_step_streamed(ba_handle* h, const double* R, const double* T, const doubl
 int ba_accept(ba_handle* h);
 int ba_reject(ba_handle* h);
 
+/* ≙ Utils::showErrorStatistics + Utils::showObjective (src/Utils.h:15-68; bundle_adjustment_large.cpp:130-131,170-171) as one GPU
+ * reduction at the device-resident state: sums[0] = sum_k avg_f |p_k - m_k|, sums[1] = the same over the inliers
+ * (error <= inlier_threshold), sums[2] = number of inliers, sums[3] = "True objective" = sum_k psi(thr^2, avg_f^2 |p_k - m_k|)
+ * (the norm, not its square, as the reference computes it). Sums over all ranks' observations. The caller divides by K / by the
+ * inlier count and prints. */
+int ba_error_statistics(ba_handle* h, double avg_focal_length, double inlier_threshold, double* sums);
+
 /* Diagnostics for parity tests (not on the hot path). dx: 3M+9N doubles; residuals: 2K;
  * reduced system of the last ba_compute BEFORE factorisation: S dense symmetric (9N)^2 row-major, g 9N. */
 int ba_get_dx(ba_handle* h, double* dx);

@@ -40,6 +40,7 @@ def test_usage_and_return_codes(binaries):
     assert r.returncode == 2 and "Cannot open" in r.stderr
 
 
+@pytest.mark.gpu
 def test_before_statistics_match_anchors(binaries, p21_txt):
     exe = os.path.join(binaries, "Bundle_Adjustment_QRChol")
     r = subprocess.run([exe, p21_txt], capture_output=True, text=True, env={**os.environ, "BA_MAX_ITERS": "1"})

@@ -484,3 +484,35 @@ def test_streamed_step_equals_separate_calls(variant, precision):
             assert (e1, dxn1, rho1, et1) == (e2, dxn2, rho2, et2), (prob.name, chunks)
             assert np.array_equal(dx1, dx2), (prob.name, chunks)
             s.close()
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_error_statistics_reduction(precision):
+    """ba_error_statistics = Utils::showErrorStatistics + showObjective (src/Utils.h:15-68) as one GPU reduction: mean reprojection
+    error, inlier mean, inlier count and the "True objective" (psi of the NORM, as the reference computes it) against numpy."""
+    prob = bal.load_named("problem-21-11315")
+    s = solver.GpuSolver(prob, "QRCHOL", precision)
+    R, T, f, k1, k2, X = [np.asarray(a, dtype=np.float64) for a in s.get_state()]
+    v, p = prob.view, prob.point
+    XX = np.einsum("kij,kj->ki", R[v], X[p]) + T[v]
+    xu = XX[:, :2] / XX[:, 2:3]
+    r2 = (xu ** 2).sum(axis=1)
+    proj = (f[v] * (1 + k1[v] * r2 + k2[v] * r2 * r2))[:, None] * xu
+    en = np.linalg.norm(proj - np.asarray(prob.meas).reshape(-1, 2), axis=1)
+    avg_f = 1234.5
+    e = avg_f * en
+    thr = float(np.median(e))            # half of the observations are inliers
+    inl = e <= thr
+    q2 = avg_f * avg_f * en
+    tau2 = thr * thr
+    obj = np.where(q2 < tau2, q2 * (3 - 3 * q2 / tau2 + q2 * q2 / tau2 ** 2) / 6, tau2 / 6).sum()
+    mean, inl_mean, n_inl, tobj = s.error_statistics(avg_f, thr)
+    tol = 1e-12 if precision == "f64" else 2e-4
+    assert abs(mean - e.mean()) / e.mean() < tol
+    assert abs(tobj - obj) / obj < tol
+    band = 1e-9 if precision == "f64" else 1e-3      # observations this close to the threshold may fall on either side
+    n_lo, n_hi = int((e <= thr * (1 - band)).sum()), int((e <= thr * (1 + band)).sum())
+    assert n_lo <= n_inl <= n_hi, (n_lo, n_inl, n_hi)
+    # small residuals carry the cancellation error of p - m: 1e-9 instead of 1e-12
+    assert abs(inl_mean - e[inl].mean()) / e[inl].mean() < (max(tol, 1e-9) if n_lo == n_hi else 1e-3), (inl_mean, e[inl].mean(), n_lo, n_hi)
+    s.close()
