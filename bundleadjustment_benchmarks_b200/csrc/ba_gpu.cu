@@ -332,7 +332,12 @@ struct Impl : ba_handle {
   int camup_blocks() const { return (N + CAMUP_THREADS - 1) / CAMUP_THREADS; }
   cudaStream_t stream2 = nullptr;   // separator split: the spike kernel runs beside the next chain segment / the middle blocks
   cudaEvent_t sev[10] = {};
+  cudaEvent_t lev[5] = {};          // launch completion events of the chain segments / middle blocks
   int split_segments = 3;
+  bool tl_deferred = false; int tl_calls = 0;
+  bool split_timeline = false; cudaEvent_t tlv[24] = {}; int tl_n = 0; const char* tl_name[24] = {};
+  bool tl_s2only = false;
+  void tl(const char* name, cudaStream_t st) { if (tl_s2only && st == stream && std::strncmp(name, "split", 5) != 0) return; if (split_timeline && tl_n < 24) { if (!tlv[tl_n]) cudaEventCreate(&tlv[tl_n]); cudaEventRecord(tlv[tl_n], st); tl_name[tl_n++] = name; } }
   // ba_step_streamed: the point coordinates are uploaded in chunks on stream2 while the point-factor kernel already works on
   // the chunks that have arrived, and dx is downloaded in chunks behind the back-substitution kernel
   static constexpr int SX_MAX = 16;
@@ -387,6 +392,7 @@ struct Impl : ba_handle {
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : tev) if (e) cudaEventDestroy(e);
     for (auto& e : sev) if (e) cudaEventDestroy(e);
+    for (auto& e : lev) if (e) cudaEventDestroy(e);
     for (auto& e : xev) if (e) cudaEventDestroy(e);
     for (auto& e : bev) if (e) cudaEventDestroy(e);
     if (stream2) cudaStreamDestroy(stream2);
@@ -532,10 +538,18 @@ struct Impl : ba_handle {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(BA_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
     CK(cudaSetDevice(device));
-    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    // When a chain segment (16-CTA clusters, each needs 16 free SMs in one GPC) and the spike kernel of the previous segment
+    // (70 plain CTAs on stream2) become ready at the same moment, the clusters must be placed first: otherwise the spike's
+    // CTAs scatter over the GPCs and the chains wait for them (measured: +0.2 ms per segment). The spike therefore also waits
+    // for the LAUNCH COMPLETION event of the next chain launch (factor_reduced_split), and stream2 has the lower priority
+    // (a higher-priority dependent may start before the launch completes).
+    int prio_least = 0, prio_greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_greatest));
     for (auto& e : ev) CK(cudaEventCreate(&e));
-    CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prio_least));
     for (auto& e : sev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : lev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : xev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : bev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (const char* sc = std::getenv("BA_STREAM_CHUNKS")) sx_chunks = std::max(1, std::min(SX_MAX, atoi(sc)));
@@ -617,6 +631,7 @@ struct Impl : ba_handle {
     if (const char* ts = std::getenv("BA_LDLT_TWOSIDED")) two_sided = atoi(ts) != 0;
     if (const char* v2 = std::getenv("BA_LDLT_V2")) ldlt_v2 = atoi(v2) != 0;
     if (const char* v3 = std::getenv("BA_LDLT_SPLIT")) ldlt_split = atoi(v3);
+    if (const char* tlm = std::getenv("BA_SPLIT_TIMELINE")) { split_timeline = true; tl_deferred = atoi(tlm) >= 2; tl_s2only = atoi(tlm) == 3; }
     if (const char* v4 = std::getenv("BA_LDLT_SPLIT_SEGMENTS")) split_segments = std::max(1, std::min(4, atoi(v4)));
     CK(cudaFuncSetAttribute(k_spike, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpikeSmem)));
     CK(cudaFuncSetAttribute(k_sep_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM));
@@ -960,6 +975,12 @@ struct Impl : ba_handle {
       const int ab = 4 * sm_count;
       // part 0 as an index-reversed copy of its own (the separator then sits above row 0 of either part)
       BandMat<T> A0{Sv(), ldv, npart[0], kd};
+      if (split_timeline && tl_deferred && tl_n > 0 && !solve_only) {   // the previous trial's events (complete: its solve_try synchronised)
+        if (cudaEventQuery(tlv[tl_n - 1]) == cudaSuccess && ++tl_calls % 8 == 0)
+          for (int i = 1; i < tl_n; ++i) { float ms = 0; cudaEventElapsedTime(&ms, tlv[0], tlv[i]); fprintf(stderr, "[split timeline] %-18s %8.3f ms\n", tl_name[i], ms); }
+        tl_n = 0;
+      }
+      tl("split begin", stream);
       if (solve_only) k_rhs_reverse<T><<<64, 256, 0, stream>>>(gvec(), gX[0], npart[0], npart[0], npart[0]);
       BandMat<T> X[2], Ar[2], Am[2];
       LdltJob<T> job = {}, mid = {};
@@ -979,6 +1000,7 @@ struct Impl : ba_handle {
         RevJob<T> rj1{A0, gvec(), Rv[0], gr[0], nph[0], r0[0], 0};
         RevJob<T> rj2{X[1], gX[1], Rv[1], gr[1], nph[1], r0[1], 1};
         k_band_reverse3<T><<<dim3(2 * sm_count, 3), 256, 0, stream>>>(rj0, rj1, rj2);
+        tl("reverse end", stream);
         CK(cudaEventRecord(sev[9], stream));
         CK(cudaStreamWaitEvent(stream2, sev[9], 0));
         for (int p = 0; p < 2; ++p) k_spike_init<<<ab / 2, 256, 0, stream2>>>(A, sp[p].E.p, ldE[p], w, (bt + 1) * NB, s0, p1, npart[p], p);
@@ -996,7 +1018,9 @@ struct Impl : ba_handle {
           const int kb = middle ? q[p] : (int)((long long)q[p] * seg0 / nseg), ke = middle ? npE[p] : (int)((long long)q[p] * seg1 / nseg);
           sj[p] = SpikeJob{BandMat<double>{Xv[p], ldv, ncolE[p], kd}, sp[p].dvec.p, sp[p].W.p, sp[p].E.p, ldE[p], kb, ke};
         }
+        tl(middle ? "spike_mid begin" : "spike begin", st);
         k_spike<<<2 * nstrips, SPK_THREADS, sizeof(SpikeSmem), st>>>(sj[0], sj[1], w, d_dbg.p);
+        tl(middle ? "spike_mid end" : "spike end", st);
         // the separator block receives the Schur complement of the same panels right away
         k_sep_syrk<<<nts * (nts + 1) / 2, 256, SYRK_SMEM, st>>>(A, s0, w, Sd, ldw, SyrkSide{sp[0].E.p, ldE[0], sp[0].dvec.p, sj[0].k_begin, sj[0].k_end},
                                                               SyrkSide{sp[1].E.p, ldE[1], sp[1].dvec.p, sj[1].k_begin, sj[1].k_end}, (!middle && seg0 == 0) ? 1 : 0);
@@ -1011,11 +1035,15 @@ struct Impl : ba_handle {
           P.dvec += (size_t)a * NB; P.Wbuf += (size_t)a * NB * NB; P.rhs += (size_t)a * NB; P.y += (size_t)a * NB;
           P.np_fwd = b - a;
         }
-        CK(launch(seg, 4));
+        tl("chain seg begin", stream);
+        const bool beside = !solve_only && sg > 0;
+        CK(launch(seg, 4, beside ? lev[sg] : nullptr));
+        tl("chain seg end", stream);
         if (!solve_only) {
           CK(cudaEventRecord(sev[sg], stream));
-          if (sg > 0) {               // spike of segment sg - 1 beside chain segment sg
+          if (sg > 0) {               // spike of segment sg - 1 beside chain segment sg, once its clusters have been placed
             CK(cudaStreamWaitEvent(stream2, sev[sg - 1], 0));
+            if (beside) CK(cudaStreamWaitEvent(stream2, lev[sg], 0));
             spike(sg - 1, sg, false, stream2);
           }
         }
@@ -1024,9 +1052,11 @@ struct Impl : ba_handle {
         if (solve_only) k_rhs_combine<T><<<8, 256, 0, stream>>>(gX[p], gr[p], npart[p], r0[p], nm[p]);
         else k_band_combine<T><<<64, 256, 0, stream>>>(X[p], gX[p], Rv[p], gr[p], r0[p], nm[p]);
       }
-      CK(launch(mid, 2));
+      CK(launch(mid, 2, !solve_only ? lev[0] : nullptr));
+      tl("mid end", stream);
       if (!solve_only) {
         CK(cudaStreamWaitEvent(stream2, sev[nseg - 1], 0));
+        CK(cudaStreamWaitEvent(stream2, lev[0], 0));
         spike(nseg - 1, nseg, false, stream2);      // beside the middle blocks
         CK(cudaEventRecord(sev[8], stream2));
         CK(cudaStreamWaitEvent(stream, sev[8], 0));
@@ -1037,7 +1067,9 @@ struct Impl : ba_handle {
       LdltJob<T> sep = {};
       sep.sign = T(-1);
       sep.p[0] = LdltProblem<T>{BandMat<T>{Sd, (size_t)ldw, w, kds}, ds, d_sep_W.p, gs, ys, d_info.p, nts, nts, fwd, 1};
+      tl("sep begin", stream);
       CK(launch(sep, 1));
+      tl("sep end", stream);
       k_spike_correct<<<dim3((std::max(ncolE[0], ncolE[1]) + 31) / 32, 2), 256, 0, stream>>>(CorrSide{sp[0].E.p, ldE[0], ncolE[0], gX[0]}, CorrSide{sp[1].E.p, ldE[1], ncolE[1], gX[1]}, w, ys, -1.0);
       for (int p = 0; p < 2; ++p) { mid.p[p].do_fwd = 0; mid.p[p].do_bwd = 1; mid.p[p].kb_bwd = ntm[p]; }
       CK(launch(mid, 2));
@@ -1051,6 +1083,12 @@ struct Impl : ba_handle {
       CK(cudaMemcpyAsync(d_dx_cam.p + s0, ys, (size_t)w * sizeof(T), cudaMemcpyDeviceToDevice, stream));
       launches += 14;
       CK(cudaGetLastError());
+      tl("split end", stream);
+      if (split_timeline && !solve_only && !tl_deferred) {
+        CK(cudaStreamSynchronize(stream)); CK(cudaStreamSynchronize(stream2));
+        for (int i = 1; i < tl_n; ++i) { float ms = 0; cudaEventElapsedTime(&ms, tlv[0], tlv[i]); fprintf(stderr, "[split timeline] %-18s %8.3f ms\n", tl_name[i], ms); }
+      }
+      if (!tl_deferred) tl_n = 0;
       done = true;
     }
     return BA_OK;
@@ -1065,13 +1103,20 @@ struct Impl : ba_handle {
       const double flops = (double)n * kd * kd;
       if (flops < 2e11 && bt <= CL_MAX_BT && !force_grid_ldlt) {
         // latency-bound regime: thread-block clusters, forward solve folded in, backward pass on the cluster
-        auto launch = [&](const LdltJob<T>& job, int nclusters) -> cudaError_t {
+        // started: recorded once all CTAs of the launch have begun execution (launch completion event; lets the spike kernel on
+        // the second stream start only after the clusters of the next chain segment have been placed)
+        auto launch = [&](const LdltJob<T>& job, int nclusters, cudaEvent_t started = nullptr) -> cudaError_t {
           cudaLaunchConfig_t cfg = {};
           cfg.gridDim = dim3(cluster_size * nclusters); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = sizeof(ClusterSmem<T>); cfg.stream = stream;
-          cudaLaunchAttribute attr[1];
+          cudaLaunchAttribute attr[2];
           attr[0].id = cudaLaunchAttributeClusterDimension;
           attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
           cfg.attrs = attr; cfg.numAttrs = 1;
+          if (started) {
+            attr[1].id = cudaLaunchAttributeLaunchCompletionEvent;
+            attr[1].val.launchCompletionEvent.event = started; attr[1].val.launchCompletionEvent.flags = 0;
+            cfg.numAttrs = 2;
+          }
           launches++;
 #ifdef BA_L2_TICKS
           return cudaLaunchKernelEx(&cfg, k_band_ldlt_cluster<T>, job, (long long*)nullptr, ldlt_roww);  // keep fwd2's counters
