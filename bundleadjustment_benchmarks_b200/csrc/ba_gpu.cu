@@ -925,6 +925,16 @@ struct Impl : ba_handle {
   // Separator split (ba_split.cuh): S = [part 0 | separator | part 1], four elimination chains side by side, spikes,
   // separator Schur complement, then the backward passes in the opposite order. Returns false when the system is too
   // small for it (the caller falls back to the two-sided scheme).
+  // first panel of chain segment j of nseg. With three or more segments the last one is a quarter of the chain: its spike and
+  // SYRK run beside the middle blocks (0.28 ms) and must not outlast them; the others share the rest evenly.
+  static int seg_bound(int q, int j, int nseg) {
+    if (j <= 0) return 0;
+    if (j >= nseg) return q;
+    if (nseg < 3) return (int)((long long)q * j / nseg);
+    const int head = q - q / 4;
+    return (int)((long long)head * j / (nseg - 1));
+  }
+
   template <class L> int factor_reduced_split(bool solve_only, L&& launch, bool& done) {
     done = false;
     if constexpr (sizeof(T) == 8) {
@@ -1015,7 +1025,7 @@ struct Impl : ba_handle {
       auto spike = [&](int seg0, int seg1, bool middle, cudaStream_t st) {
         SpikeJob sj[2];
         for (int p = 0; p < 2; ++p) {
-          const int kb = middle ? q[p] : (int)((long long)q[p] * seg0 / nseg), ke = middle ? npE[p] : (int)((long long)q[p] * seg1 / nseg);
+          const int kb = middle ? q[p] : seg_bound(q[p], seg0, nseg), ke = middle ? npE[p] : seg_bound(q[p], seg1, nseg);
           sj[p] = SpikeJob{BandMat<double>{Xv[p], ldv, ncolE[p], kd}, sp[p].dvec.p, sp[p].W.p, sp[p].E.p, ldE[p], kb, ke};
         }
         tl(middle ? "spike_mid begin" : "spike begin", st);
@@ -1029,7 +1039,7 @@ struct Impl : ba_handle {
       for (int sg = 0; sg < nseg; ++sg) {
         LdltJob<T> seg = job;
         for (int c = 0; c < 4; ++c) {
-          const int p = c / 2, a = (int)((long long)q[p] * sg / nseg), b = (int)((long long)q[p] * (sg + 1) / nseg);
+          const int p = c / 2, a = seg_bound(q[p], sg, nseg), b = seg_bound(q[p], sg + 1, nseg);
           LdltProblem<T>& P = seg.p[c];
           P.A = BandMat<T>{P.A.v + (size_t)a * NB * (ldv + 1), ldv, P.A.n - a * NB, kd};
           P.dvec += (size_t)a * NB; P.Wbuf += (size_t)a * NB * NB; P.rhs += (size_t)a * NB; P.y += (size_t)a * NB;
