@@ -1022,7 +1022,9 @@ struct Impl : ba_handle {
       const int nseg = solve_only ? 1 : split_segments;
       const int ncolE[2] = {r0[0] + nm[0], r0[1] + nm[1]};
       const int nstrips = (w + SPK_STRIP - 1) / SPK_STRIP;
-      auto spike = [&](int seg0, int seg1, bool middle, cudaStream_t st) {
+      // after_spike: recorded between the spike and its SYRK; before_syrk: the SYRK waits for it (the SYRKs accumulate into the
+      // same block and must stay ordered)
+      auto spike = [&](int seg0, int seg1, bool middle, cudaStream_t st, cudaEvent_t after_spike = nullptr, cudaEvent_t before_syrk = nullptr) -> cudaError_t {
         SpikeJob sj[2];
         for (int p = 0; p < 2; ++p) {
           const int kb = middle ? q[p] : seg_bound(q[p], seg0, nseg), ke = middle ? npE[p] : seg_bound(q[p], seg1, nseg);
@@ -1031,10 +1033,13 @@ struct Impl : ba_handle {
         tl(middle ? "spike_mid begin" : "spike begin", st);
         k_spike<<<2 * nstrips, SPK_THREADS, sizeof(SpikeSmem), st>>>(sj[0], sj[1], w, d_dbg.p);
         tl(middle ? "spike_mid end" : "spike end", st);
+        if (after_spike) { cudaError_t e = cudaEventRecord(after_spike, st); if (e != cudaSuccess) return e; }
+        if (before_syrk) { cudaError_t e = cudaStreamWaitEvent(st, before_syrk, 0); if (e != cudaSuccess) return e; }
         // the separator block receives the Schur complement of the same panels right away
         k_sep_syrk<<<nts * (nts + 1) / 2, 256, SYRK_SMEM, st>>>(A, s0, w, Sd, ldw, SyrkSide{sp[0].E.p, ldE[0], sp[0].dvec.p, sj[0].k_begin, sj[0].k_end},
                                                               SyrkSide{sp[1].E.p, ldE[1], sp[1].dvec.p, sj[1].k_begin, sj[1].k_end}, (!middle && seg0 == 0) ? 1 : 0);
         launches += 2;
+        return cudaSuccess;
       };
       for (int sg = 0; sg < nseg; ++sg) {
         LdltJob<T> seg = job;
@@ -1054,7 +1059,7 @@ struct Impl : ba_handle {
           if (sg > 0) {               // spike of segment sg - 1 beside chain segment sg, once its clusters have been placed
             CK(cudaStreamWaitEvent(stream2, sev[sg - 1], 0));
             if (beside) CK(cudaStreamWaitEvent(stream2, lev[sg], 0));
-            spike(sg - 1, sg, false, stream2);
+            CK(spike(sg - 1, sg, false, stream2));
           }
         }
       }
@@ -1067,10 +1072,10 @@ struct Impl : ba_handle {
       if (!solve_only) {
         CK(cudaStreamWaitEvent(stream2, sev[nseg - 1], 0));
         CK(cudaStreamWaitEvent(stream2, lev[0], 0));
-        spike(nseg - 1, nseg, false, stream2);      // beside the middle blocks
+        CK(spike(nseg - 1, nseg, false, stream2, sev[7]));   // beside the middle blocks
         CK(cudaEventRecord(sev[8], stream2));
-        CK(cudaStreamWaitEvent(stream, sev[8], 0));
-        spike(0, 0, true, stream);                  // the middle panels
+        CK(cudaStreamWaitEvent(stream, sev[7], 0));          // the middle panels' spike needs the last segment's spike,
+        CK(spike(0, 0, true, stream, nullptr, sev[8]));      // their SYRK the last segment's SYRK
       }
       k_sep_rhs<<<w, 256, 0, stream>>>(gvec(), s0, w, gs, RhsSide{sp[0].E.p, ldE[0], sp[0].dvec.p, gX[0], ncolE[0]},
                                                  RhsSide{sp[1].E.p, ldE[1], sp[1].dvec.p, gX[1], ncolE[1]});
