@@ -203,3 +203,22 @@ def test_fully_saturated_kernel_is_finite():
     assert abs(e - p.K * 0.0625) < 1e-12
     ok, dx = o.step(QRCHOL, 1e-12 * cn2)
     assert ok and np.isfinite(dx).all()
+
+
+def test_anchors_follow_from_independent_restatement():
+    """tests/golden/make_golden.py derives the stored anchors without any code shared with the oracle or the CUDA library:
+    NumPy residuals, complex-step Jacobian, SciPy sparse normal equations for the first LM step (cond ~ 1e12: 1e-7)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    name = "problem-21-11315"
+    a, g = mg.anchors(name, True), GOLD[name]
+    assert (a["N"], a["M"], a["K"], a["initial_inliers"]) == (g["N"], g["M"], g["K"], g["initial_inliers"])
+    for key, tol in (("initial_energy", 1e-11), ("max_colnorm2", 1e-8), ("max_colnorm", 1e-8), ("initial_mean_reproj_px", 1e-6),
+                     ("iter1_dx_norm", 1e-8), ("iter1_energy_test", 1e-7)):
+        assert abs(a[key] - g[key]) / abs(g[key]) < tol, (key, a[key], g[key])
+    # and the oracle agrees with the restatement beyond the digits that were stored
+    o = Oracle(bal.load_named(name))
+    e, cn2, cn = o.linearize()
+    assert abs(e - a["initial_energy"]) / e < 1e-12 and abs(cn2 - a["max_colnorm2"]) / cn2 < 1e-12
