@@ -265,11 +265,11 @@ def run_ours(args):
     lam = 1e-6 * cn if args.variant == "MOREQR" else 1e-12 * cn2
 
     def step():
-        s.linearize(colnorms=False)
-        s.compute(lam)
-        out = s.solve_try()
+        # energy + compute(lam) + solve_try on the device-resident state in one call (one host synchronisation per step);
+        # bit-identical to ba_linearize + ba_compute + ba_solve_try (tests/test_gpu_parity.py)
+        out = s.step_resident(lam)
         s.reject()
-        return out
+        return out[1:]
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

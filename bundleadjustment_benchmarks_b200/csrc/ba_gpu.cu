@@ -715,13 +715,27 @@ struct Impl : ba_handle {
   int step_streamed(const double* R, const double* Tt, const double* f, const double* k1, const double* k2, const double* X, double lam,
                     double* dx, double* energy, double* dx_norm, double* rho_den, double* energy_test) override {
     CK(cudaSetDevice(device));
+    if (R && (!Tt || !f || !k1 || !k2 || !X)) return fail(BA_ERR_ARG, "ba_step_streamed: pass all six state arrays or none");
     if (sizeof(T) != sizeof(double) || two_stage) {
-      int rc = set_state(R, Tt, f, k1, k2, X);
+      int rc = R ? set_state(R, Tt, f, k1, k2, X) : BA_OK;
       if (!rc) rc = linearize(energy, nullptr, nullptr);
       if (!rc) rc = compute(lam);
       if (!rc) rc = solve_try(dx_norm, rho_den, energy_test);
       if (!rc && dx) rc = get_dx(dx);
       return rc;
+    }
+    if (!R) {   // state already resident on the device: energy + compute + solve_try (+ download) with a single synchronisation
+      computed = tried = false;
+      int rc = compute(lam);
+      if (!rc) rc = energy_pass(0);
+      if (rc) return rc;
+      linearized = true;
+      dx_sink = dx;
+      rc = solve_try(dx_norm, rho_den, energy_test);
+      dx_sink = nullptr;
+      if (rc) return rc;
+      if (energy) *energy = h_scal[0];
+      return BA_OK;
     }
     const size_t nc = (size_t)N * CAM_STRIDE;
     { int rc = stage_buf(nc); if (rc) return rc; }

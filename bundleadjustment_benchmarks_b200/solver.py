@@ -159,6 +159,15 @@ class GpuSolver:
         self._ck(self._L.ba_error_statistics(self._h, float(avg_focal_length), float(inlier_threshold), _dp(out)))
         return out[0] / self.K, (out[1] / out[2] if out[2] > 0 else float("nan")), int(out[2]), out[3]
 
+    def step_resident(self, lam, dx_out=None):
+        """ba_step_streamed on the state already on the device: (energy, |dx|, rho denominator, test energy), one synchronisation."""
+        if dx_out is not None:
+            assert dx_out.dtype == np.float64 and dx_out.size == self.n and dx_out.flags["C_CONTIGUOUS"]
+        e, a, b, c = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        self._ck(self._L.ba_step_streamed(self._h, None, None, None, None, None, None, float(lam), _dp(dx_out) if dx_out is not None else None,
+                                          C.byref(e), C.byref(a), C.byref(b), C.byref(c)))
+        return e.value, a.value, b.value, c.value
+
     def dx_into(self, out):
         """Step download into a caller-owned (ideally pinned) float64 buffer of 3M+9N entries."""
         assert out.dtype == np.float64 and out.size == self.n and out.flags["C_CONTIGUOUS"]

@@ -101,7 +101,8 @@ int ba_set_strict_numeric(ba_handle* h, int enable);
  * point stage: the point coordinates go up in chunks while the point-factor kernel works on the chunks that have arrived, and dx
  * comes down in chunks behind the back-substitution kernel. Results are bit-identical to the separate calls. dx: 3M+9N doubles
  * (may be NULL: no download). The host buffers should be page-locked (otherwise the copies do not overlap) and must stay valid
- * until the call returns; it blocks like ba_solve_try. Float build / MOREQR two-stage: runs the separate calls in sequence. */
+ * until the call returns; it blocks like ba_solve_try. Float build / MOREQR two-stage: runs the separate calls in sequence.
+ * R = T = f = k1 = k2 = X = NULL: the state already on the device is used (energy + compute + solve_try with one synchronisation). */
 int ba_step_streamed(ba_handle* h, const double* R, const double* T, const double* f, const double* k1, const double* k2, const double* X,
                      double lambda, double* dx, double* energy, double* dx_norm, double* rho_den, double* energy_test);
 

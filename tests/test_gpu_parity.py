@@ -483,6 +483,9 @@ def test_streamed_step_equals_separate_calls(variant, precision):
             s.reject()
             assert (e1, dxn1, rho1, et1) == (e2, dxn2, rho2, et2), (prob.name, chunks)
             assert np.array_equal(dx1, dx2), (prob.name, chunks)
+            dx2[:] = np.nan
+            assert s.step_resident(lam, dx2) == (e1, dxn1, rho1, et1) and np.array_equal(dx1, dx2)   # state already on the device
+            s.reject()
             s.close()
 
 
