@@ -91,7 +91,9 @@ int ba_solve_try(ba_handle* h, double* dx_norm, double* rho_denominator, double*
  * system yields a non-finite test energy, which `energyTest < m_energy` (QRChol.h:374) treats as a rejected trial.
  * Same here: on a zero/NaN pivot or a non-finite step ba_solve_try still returns BA_OK but reports energy_test = NaN,
  * and *info says why: 0 = fine, r > 0 = zero or NaN pivot at (1-based) row r of the reduced camera system,
- * -1 = non-finite step. After ba_set_strict_numeric(h, 1) such a trial makes ba_solve_try fail with BA_ERR_NUMERIC. */
+ * -1 = non-finite step. (With the two-sided / separator-split factorisations r counts rows inside the block that was being
+ * eliminated - a chain, a middle block or the separator - not rows of the whole system.) After ba_set_strict_numeric(h, 1) such a
+ * trial makes ba_solve_try fail with BA_ERR_NUMERIC. */
 int ba_numeric_status(ba_handle* h, int* info);
 int ba_set_strict_numeric(ba_handle* h, int enable);
 
