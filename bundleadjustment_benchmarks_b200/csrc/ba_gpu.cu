@@ -1077,10 +1077,8 @@ struct Impl : ba_handle {
           }
         }
       }
-      for (int p = 0; p < 2; ++p) {
-        if (solve_only) k_rhs_combine<T><<<8, 256, 0, stream>>>(gX[p], gr[p], npart[p], r0[p], nm[p]);
-        else k_band_combine<T><<<64, 256, 0, stream>>>(X[p], gX[p], Rv[p], gr[p], r0[p], nm[p]);
-      }
+      k_band_combine2<T><<<dim3(solve_only ? 8 : 64, 2), 256, 0, stream>>>(CombJob<T>{X[0], gX[0], Rv[0], gr[0], r0[0], nm[0]},
+                                                                         CombJob<T>{X[1], gX[1], Rv[1], gr[1], r0[1], nm[1]}, solve_only ? 1 : 0);
       CK(launch(mid, 2, !solve_only ? lev[0] : nullptr));
       tl("mid end", stream);
       if (!solve_only) {
@@ -1102,15 +1100,12 @@ struct Impl : ba_handle {
       k_spike_correct<<<dim3((std::max(ncolE[0], ncolE[1]) + 31) / 32, 2), 256, 0, stream>>>(CorrSide{sp[0].E.p, ldE[0], ncolE[0], gX[0]}, CorrSide{sp[1].E.p, ldE[1], ncolE[1], gX[1]}, w, ys, -1.0);
       for (int p = 0; p < 2; ++p) { mid.p[p].do_fwd = 0; mid.p[p].do_bwd = 1; mid.p[p].kb_bwd = ntm[p]; }
       CK(launch(mid, 2));
-      for (int p = 0; p < 2; ++p) {
-        k_flip_copy<T><<<8, 256, 0, stream>>>(sp[p].y2.p, yX[p], npart[p], r0[p], nph[p]);
+      k_flip_copy2<T><<<dim3(8, 2), 256, 0, stream>>>(FlipJob<T>{sp[0].y2.p, yX[0], npart[0], r0[0], nph[0]}, FlipJob<T>{sp[1].y2.p, yX[1], npart[1], r0[1], nph[1]});
+      for (int p = 0; p < 2; ++p)
         for (int c = 0; c < 2; ++c) { job.p[2 * p + c].do_fwd = 0; job.p[2 * p + c].do_bwd = 1; job.p[2 * p + c].kb_bwd = q[p]; }
-      }
       CK(launch(job, 4));
-      for (int p = 0; p < 2; ++p) k_flip_copy<T><<<32, 256, 0, stream>>>(yX[p], sp[p].y2.p, npart[p], r0[p] + nm[p], npart[p]);
-      k_flip_copy<T><<<32, 256, 0, stream>>>(d_dx_cam.p, yX[0], npart[0], 0, npart[0]);
-      CK(cudaMemcpyAsync(d_dx_cam.p + s0, ys, (size_t)w * sizeof(T), cudaMemcpyDeviceToDevice, stream));
-      launches += 14;
+      k_split_assemble<T><<<64, 256, 0, stream>>>(d_dx_cam.p, n, s0, p1, yX[0], sp[0].y2.p, r0[0] + nm[0], ys, sp[1].y2.p, r0[1] + nm[1]);
+      launches += 10;
       CK(cudaGetLastError());
       tl("split end", stream);
       if (split_timeline && !solve_only && !tl_deferred) {

@@ -403,20 +403,77 @@ __global__ void __launch_bounds__(256) k_spike_correct(CorrSide c0, CorrSide c1,
 // The three index-reversed copies of the split in one launch (k_band_reverse for each job; they are independent: the
 // reversed half of the index-reversed part 0 is the top of part 0 as it stands).
 template <class T> struct RevJob { BandMat<T> A; const T* g; T* Rv; T* gr; int np, mrow0, flip; };   // flip = 0: plain copy of the top np rows
+// blockIdx.y = job; blockIdx.x walks 32 x 32 tiles (tile row bi, tile diagonal dj) of the output band. A flipped tile is read
+// along the input's rows (coalesced) and transposed through shared memory; the plain copy needs no transpose.
 template <class T>
-__global__ void k_band_reverse3(RevJob<T> j0, RevJob<T> j1, RevJob<T> j2) {
+__global__ void __launch_bounds__(256) k_band_reverse3(RevJob<T> j0, RevJob<T> j1, RevJob<T> j2) {
+  __shared__ T tile[32][33];
   const RevJob<T>& J = blockIdx.y == 0 ? j0 : (blockIdx.y == 1 ? j1 : j2);
   const int n = J.A.n, kd = J.A.kd, np = J.np, mrow0 = J.mrow0;
-  const size_t lds = J.A.lds, total = (size_t)np * (kd + 1), stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int ip = (int)(idx / (kd + 1)), d = (int)(idx - (size_t)ip * (kd + 1)), jp = ip - d;
-    if (jp < 0) continue;
-    T v = T(0);
-    if (!(ip >= mrow0 && jp >= mrow0)) v = J.flip ? J.A.v[(size_t)(n - 1 - jp) * lds + (n - 1 - ip)] : J.A.v[(size_t)ip * lds + jp];
-    J.Rv[(size_t)ip * lds + jp] = v;
+  const size_t lds = J.A.lds;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ntr = (np + 31) / 32, ndj = (kd + 31) / 32 + 1;
+  for (int t = blockIdx.x; t < ntr * ndj; t += gridDim.x) {
+    const int bi = t / ndj, dj = t - bi * ndj, bj = bi - dj;
+    if (bj < 0) continue;
+    const int i0 = 32 * bi, c0 = 32 * bj;
+    if (J.flip) {
+      // tile[c][r] = A(n-1-(c0+c), n-1-(i0+r)): consecutive r -> consecutive (descending) input addresses
+      for (int c = ty; c < 32; c += 8) {
+        const int ip = i0 + tx, jp = c0 + c;
+        const bool ok = ip < np && jp <= ip && ip - jp <= kd && !(ip >= mrow0 && jp >= mrow0);
+        tile[c][tx] = ok ? J.A.v[(size_t)(n - 1 - jp) * lds + (n - 1 - ip)] : T(0);
+      }
+      __syncthreads();
+      for (int r = ty; r < 32; r += 8) {
+        const int ip = i0 + r, jp = c0 + tx;
+        if (ip < np && jp <= ip && ip - jp <= kd) J.Rv[(size_t)ip * lds + jp] = tile[tx][r];
+      }
+      __syncthreads();
+    } else {
+      for (int r = ty; r < 32; r += 8) {
+        const int ip = i0 + r, jp = c0 + tx;
+        if (ip < np && jp <= ip && ip - jp <= kd) J.Rv[(size_t)ip * lds + jp] = (ip >= mrow0 && jp >= mrow0) ? T(0) : J.A.v[(size_t)ip * lds + jp];
+      }
+    }
   }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)np; i += stride)
     J.gr[i] = ((int)i < mrow0) ? (J.flip ? J.g[n - 1 - i] : J.g[i]) : T(0);
+}
+
+// both parts' middle blocks in one launch (k_band_combine / k_rhs_combine per job, blockIdx.y = part)
+template <class T> struct CombJob { BandMat<T> A; T* g; const T* Rv; const T* gr; int r0, nm; };
+template <class T>
+__global__ void k_band_combine2(CombJob<T> j0, CombJob<T> j1, int rhs_only) {
+  const CombJob<T>& J = blockIdx.y ? j1 : j0;
+  const int n = J.A.n, kd = J.A.kd, r0 = J.r0, nm = J.nm;
+  const size_t lds = J.A.lds, total = rhs_only ? 0 : (size_t)nm * (kd + 1), stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int i = r0 + (int)(idx / (kd + 1)), d = (int)(idx % (kd + 1)), j = i - d;
+    if (j < r0) continue;
+    J.A.v[(size_t)i * lds + j] += J.Rv[(size_t)(n - 1 - j) * lds + (n - 1 - i)];
+  }
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < (size_t)nm; t += stride) J.g[r0 + t] += J.gr[n - 1 - (r0 + (int)t)];
+}
+// y'(i') = y(n-1-i') on the middle rows of both parts' reversed halves (before the chains' backward passes)
+template <class T> struct FlipJob { T* dst; const T* src; int n, i0, i1; };
+template <class T>
+__global__ void k_flip_copy2(FlipJob<T> j0, FlipJob<T> j1) {
+  const FlipJob<T>& J = blockIdx.y ? j1 : j0;
+  for (int i = J.i0 + blockIdx.x * blockDim.x + threadIdx.x; i < J.i1; i += gridDim.x * blockDim.x) J.dst[i] = J.src[J.n - 1 - i];
+}
+// Solution of the whole system from the pieces: part 0 lives index-reversed (its bottom rows in the reversed half's y'), the
+// separator in ys, the bottom rows of part 1 in its reversed half's y'; the top of part 1 is already in place.
+template <class T>
+__global__ void k_split_assemble(T* __restrict__ out, int n, int s0, int p1, const T* __restrict__ y0, const T* __restrict__ y20, int top0,
+                                 const T* __restrict__ ys, const T* __restrict__ y21, int top1) {
+  const int n0 = s0, n1 = n - p1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i < n0) { const int j = n0 - 1 - i; out[i] = (j < top0) ? y0[j] : y20[i]; }
+    else if (i < p1) out[i] = ys[i - s0];
+    else { const int j = i - p1; if (j >= top1) out[i] = y21[n1 - 1 - j]; }
+  }
 }
 
 }  // namespace ba
