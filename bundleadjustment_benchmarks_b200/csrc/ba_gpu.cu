@@ -172,8 +172,13 @@ __global__ void __launch_bounds__(128) k_colnorm_cam(const int* __restrict__ cam
 __global__ void __launch_bounds__(1024) k_reduce(const double* __restrict__ partials, int count, double* __restrict__ out) {
   __shared__ double s[1024];
   const double* p = partials + (size_t)blockIdx.x * count;
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < count; i += blockDim.x) acc += p[i];
+  // four independent running sums per thread keep four loads in flight (fixed order: deterministic)
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  const int bd = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 3 * bd < count; i += 4 * bd) { a0 += p[i]; a1 += p[i + bd]; a2 += p[i + 2 * bd]; a3 += p[i + 3 * bd]; }
+  for (; i < count; i += bd) a0 += p[i];
+  const double acc = (a0 + a1) + (a2 + a3);
   s[threadIdx.x] = acc;
   __syncthreads();
   for (int off = blockDim.x / 2; off > 0; off >>= 1) { if ((int)threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off]; __syncthreads(); }
@@ -1023,7 +1028,7 @@ struct Impl : ba_handle {
         RevJob<T> rj0{A0, gvec(), Xv[0], gX[0], npart[0], npart[0], 1};
         RevJob<T> rj1{A0, gvec(), Rv[0], gr[0], nph[0], r0[0], 0};
         RevJob<T> rj2{X[1], gX[1], Rv[1], gr[1], nph[1], r0[1], 1};
-        k_band_reverse3<T><<<dim3(2 * sm_count, 3), 256, 0, stream>>>(rj0, rj1, rj2);
+        k_band_reverse3<T><<<dim3(8 * sm_count, 3), 256, 0, stream>>>(rj0, rj1, rj2);
         tl("reverse end", stream);
         CK(cudaEventRecord(sev[9], stream));
         CK(cudaStreamWaitEvent(stream2, sev[9], 0));
