@@ -358,7 +358,7 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get(f"{args.workload}:{args.variant}:{args.precision}", {}).get(dom)
         except Exception:
             traffic = None
-    kernel_name = {"factor": "k_band_ldlt_cluster",
+    kernel_name = {"factor": "k_band_ldlt_cluster (band LDL^T stage: separator split = 7 launches of it + k_spike / k_sep_syrk beside them)",
                    "reduced_solve": "k_band_ldlt_cluster (solve folded in)" if args.variant in ("QRCHOL", "CHOLESKY") else "k_csne_point + k_csne_cam + k_band_ldlt_cluster (refinement solve)",
                    "k_schur_gather": "k_schur_diag + k_schur_gather"}.get(dom, dom)
     n_red = 9 * N
