@@ -944,6 +944,15 @@ struct Impl : ba_handle {
   // Separator split (ba_split.cuh): S = [part 0 | separator | part 1], four elimination chains side by side, spikes,
   // separator Schur complement, then the backward passes in the opposite order. Returns false when the system is too
   // small for it (the caller falls back to the two-sided scheme).
+  // Rows the middle block of the two-sided scheme must keep: the last panel of either chain updates the rows up to kd below
+  // it, and those must not have been eliminated by the other chain, so n - 2 q NB >= kd + 1 (BA_LDLT_MID_PANELS=1 restores the
+  // earlier, tile-granular (bt + 2) * NB).
+  static int mid_rows_min(int kd_) {
+    static const bool wide = std::getenv("BA_LDLT_MID_PANELS") != nullptr;
+    const int bt_ = (kd_ + NB - 1) / NB;
+    return wide ? (bt_ + 2) * NB : kd_ + 1;
+  }
+
   // first panel of chain segment j of nseg. With three or more segments the last one is a quarter of the chain: its spike and
   // SYRK run beside the middle blocks (0.28 ms) and must not outlast them; the others share the rest evenly.
   static int seg_bound(int q, int j, int nseg) {
@@ -964,7 +973,7 @@ struct Impl : ba_handle {
       const int npart[2] = {s0, n - p1};
       int q[2], r0[2], nm[2], nph[2], ntm[2], npE[2], ldE[2];
       for (int p = 0; p < 2; ++p) {
-        q[p] = (npart[p] - (bt + 2) * NB) / (2 * NB);
+        q[p] = (npart[p] - mid_rows_min(kd)) / (2 * NB);
         // shorter chains do not pay for the extra stages (middle blocks, spike, separator: about 60 panel times at bt = 18)
         if (q[p] < bt + 2 || (ldlt_split < 2 && q[p] < 2 * bt + 8)) return BA_OK;
         r0[p] = q[p] * NB; nm[p] = npart[p] - 2 * r0[p]; nph[p] = npart[p] - r0[p];
@@ -1164,7 +1173,7 @@ struct Impl : ba_handle {
           return launch_fwd2_impl(cfg, job, d_dbg.p);
         };
         if (d_W.n < (size_t)nt * NB * NB) CK(d_W.alloc((size_t)nt * NB * NB));
-        const int q = (n - (bt + 2) * NB) / (2 * NB);  // panels eliminated from either end by the two-sided scheme
+        const int q = (n - mid_rows_min(kd)) / (2 * NB);  // panels eliminated from either end by the two-sided scheme
         bool split_done = false;
         if (two_sided && ldlt_split && cluster_size == 16) { int rc = factor_reduced_split(solve_only, launch, split_done); if (rc) return rc; }
         if (split_done) {
