@@ -20,7 +20,7 @@ _SRC = [os.path.join(_HERE, "csrc", n) for n in
 SYMBOLS = [
     "ba_last_error", "ba_version", "ba_create", "ba_destroy", "ba_comm_unique_id", "ba_comm_init",
     "ba_bandwidth", "ba_set_bandwidth", "ba_set_state", "ba_get_state", "ba_eval", "ba_linearize",
-    "ba_compute", "ba_solve_try", "ba_accept", "ba_reject", "ba_get_dx", "ba_step_streamed", "ba_error_statistics", "ba_get_residuals",
+    "ba_compute", "ba_solve_try", "ba_accept", "ba_reject", "ba_get_dx", "ba_step_streamed", "ba_error_statistics", "ba_split_plan", "ba_get_residuals",
     "ba_get_reduced_system", "ba_keep_reduced_system", "ba_get_jacobian", "ba_launch_count",
     "ba_stage_ms", "ba_set_profiling", "ba_timer_start", "ba_timer_stop", "ba_debug_counters",
     "ba_debug_band_solve", "ba_numeric_status", "ba_set_strict_numeric", "ba_debug_counters_n",
@@ -74,6 +74,7 @@ def lib():
     L.ba_reject.argtypes = [vp]
     L.ba_get_dx.argtypes = [vp, dp]
     L.ba_error_statistics.argtypes = [vp, C.c_double, C.c_double, dp]
+    L.ba_split_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int]
     L.ba_step_streamed.argtypes = [vp, dp, dp, dp, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp]
     L.ba_get_residuals.argtypes = [vp, dp]
     L.ba_get_reduced_system.argtypes = [vp, dp, dp]

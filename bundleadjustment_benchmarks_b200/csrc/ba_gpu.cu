@@ -944,42 +944,17 @@ struct Impl : ba_handle {
   // Separator split (ba_split.cuh): S = [part 0 | separator | part 1], four elimination chains side by side, spikes,
   // separator Schur complement, then the backward passes in the opposite order. Returns false when the system is too
   // small for it (the caller falls back to the two-sided scheme).
-  // Rows the middle block of the two-sided scheme must keep: the last panel of either chain updates the rows up to kd below
-  // it, and those must not have been eliminated by the other chain, so n - 2 q NB >= kd + 1 (BA_LDLT_MID_PANELS=1 restores the
-  // earlier, tile-granular (bt + 2) * NB).
-  static int mid_rows_min(int kd_) {
-    static const bool wide = std::getenv("BA_LDLT_MID_PANELS") != nullptr;
-    const int bt_ = (kd_ + NB - 1) / NB;
-    return wide ? (bt_ + 2) * NB : kd_ + 1;
-  }
-
-  // first panel of chain segment j of nseg. With three or more segments the last one is a quarter of the chain: its spike and
-  // SYRK run beside the middle blocks (0.28 ms) and must not outlast them; the others share the rest evenly.
-  static int seg_bound(int q, int j, int nseg) {
-    if (j <= 0) return 0;
-    if (j >= nseg) return q;
-    if (nseg < 3) return (int)((long long)q * j / nseg);
-    const int head = q - q / 4;
-    return (int)((long long)head * j / (nseg - 1));
-  }
-
   template <class L> int factor_reduced_split(bool solve_only, L&& launch, bool& done) {
     done = false;
     if constexpr (sizeof(T) == 8) {
       const int fwd = solve_only ? 2 : 1;
       const int bt = (kd + NB - 1) / NB;
-      int w = kd + 1; if (w & 1) ++w;
-      const int s0 = ((n - w) / 2) & ~1, p1 = s0 + w;
-      const int npart[2] = {s0, n - p1};
+      const SplitPlan pl = split_plan(n, kd, ldlt_split);
+      if (!pl.ok) return BA_OK;
+      const int w = pl.w, s0 = pl.s0, p1 = pl.p1;
+      const int npart[2] = {pl.npart[0], pl.npart[1]};
       int q[2], r0[2], nm[2], nph[2], ntm[2], npE[2], ldE[2];
-      for (int p = 0; p < 2; ++p) {
-        q[p] = (npart[p] - mid_rows_min(kd)) / (2 * NB);
-        // shorter chains do not pay for the extra stages (middle blocks, spike, separator: about 60 panel times at bt = 18)
-        if (q[p] < bt + 2 || (ldlt_split < 2 && q[p] < 2 * bt + 8)) return BA_OK;
-        r0[p] = q[p] * NB; nm[p] = npart[p] - 2 * r0[p]; nph[p] = npart[p] - r0[p];
-        ntm[p] = (nm[p] + NB - 1) / NB; npE[p] = q[p] + ntm[p]; ldE[p] = npE[p] * NB;
-      }
-      if (bt > SPK_MAX_BT || (w - 1 + NB - 1) / NB > CL_MAX_BT) return BA_OK;
+      for (int p = 0; p < 2; ++p) { q[p] = pl.q[p]; r0[p] = pl.r0[p]; nm[p] = pl.nm[p]; nph[p] = pl.nph[p]; ntm[p] = pl.ntm[p]; npE[p] = pl.npE[p]; ldE[p] = pl.ldE[p]; }
       BandMat<T> A = band();
       const size_t ldv = lds();
       T* Xv[2]; T* gX[2]; T* yX[2]; T* Rv[2]; T* gr[2];
@@ -1618,6 +1593,15 @@ int ba_get_dx(ba_handle* h, double* dx) { H_CHECK; return h->get_dx(dx); }
 int ba_step_streamed(ba_handle* h, const double* R, const double* T, const double* f, const double* k1, const double* k2, const double* X, double lambda,
                      double* dx, double* energy, double* dx_norm, double* rho_den, double* energy_test) {
   H_CHECK; return h->step_streamed(R, T, f, k1, k2, X, lambda, dx, energy, dx_norm, rho_den, energy_test);
+}
+int ba_split_plan(int n, int kd, int mode, int segments, int* out, int out_len) {
+  if (!out || out_len < 24 || n <= 0 || kd <= 0) return BA_ERR_ARG;
+  const SplitPlan pl = split_plan(n, kd, mode);
+  const int nseg = std::max(1, std::min(4, segments));
+  int v[24] = {pl.ok, pl.w, pl.s0, pl.p1, pl.npart[0], pl.npart[1], pl.q[0], pl.q[1], pl.nm[0], pl.nm[1], pl.ntm[0], pl.ntm[1], pl.npE[0], pl.npE[1], nseg};
+  for (int j = 0; j <= nseg; ++j) v[15 + j] = pl.ok ? seg_bound(pl.q[0], j, nseg) : 0;
+  for (int i = 0; i < 24; ++i) out[i] = v[i];
+  return BA_OK;
 }
 int ba_error_statistics(ba_handle* h, double avg_focal_length, double inlier_threshold, double* sums) { H_CHECK; if (!sums) return BA_ERR_ARG; return h->error_statistics(avg_focal_length, inlier_threshold, sums); }
 int ba_get_residuals(ba_handle* h, double* r) { H_CHECK; return h->get_residuals(r); }

@@ -22,6 +22,7 @@
 // w_p -= E_p^T y_sep. Reference interface: this replaces the same Eigen::SimplicialLDLT / band solve as the one- and
 // two-sided kernels (QRChol.h:197-206); the elimination order is the solver's own business.
 #pragma once
+#include <cstdlib>
 #include "ba_dense.cuh"
 
 namespace ba {
@@ -474,6 +475,48 @@ __global__ void k_split_assemble(T* __restrict__ out, int n, int s0, int p1, con
     else if (i < p1) out[i] = ys[i - s0];
     else { const int j = i - p1; if (j >= top1) out[i] = y21[n1 - 1 - j]; }
   }
+}
+
+// ---- host-side plan of the separator split (pure arithmetic: testable without a GPU through ba_split_plan)
+// Rows the middle block of the two-sided scheme must keep: the last panel of either chain updates the rows up to kd below it,
+// and those must not have been eliminated by the other chain, so n - 2 q NB >= kd + 1 (BA_LDLT_MID_PANELS=1 restores the earlier,
+// tile-granular (bt + 2) * NB).
+inline int mid_rows_min(int kd) {
+  static const bool wide = std::getenv("BA_LDLT_MID_PANELS") != nullptr;
+  const int bt = (kd + NB - 1) / NB;
+  return wide ? (bt + 2) * NB : kd + 1;
+}
+// first panel of chain segment j of nseg. With three or more segments the last one is a quarter of the chain: its spike and SYRK
+// run beside the middle blocks and must not outlast them; the others share the rest evenly.
+inline int seg_bound(int q, int j, int nseg) {
+  if (j <= 0) return 0;
+  if (j >= nseg) return q;
+  if (nseg < 3) return (int)((long long)q * j / nseg);
+  const int head = q - q / 4;
+  return (int)((long long)head * j / (nseg - 1));
+}
+// S = [part 0 : 0..s0) [separator : s0..p1) [part 1 : p1..n): separator of w >= kd + 1 rows (even, so that part 1 starts 16-byte
+// aligned), parts as equal as possible; per part q panels per chain, a middle block of nm rows (ntm panels), nph rows in the
+// reversed half, npE panels (ldE columns) of spike. mode: 0 off, 1 only when both chains are long enough to pay for the extra
+// stages (middle blocks, spike, separator: about 60 panel times at bt = 18), 2 whenever possible.
+struct SplitPlan { int ok, w, s0, p1, npart[2], q[2], r0[2], nm[2], nph[2], ntm[2], npE[2], ldE[2]; };
+inline SplitPlan split_plan(int n, int kd, int mode) {
+  SplitPlan pl = {};
+  if (mode <= 0 || n <= 0 || kd <= 0) return pl;
+  const int bt = (kd + NB - 1) / NB;
+  int w = kd + 1; if (w & 1) ++w;
+  if (n <= w) return pl;
+  pl.w = w; pl.s0 = ((n - w) / 2) & ~1; pl.p1 = pl.s0 + w;
+  pl.npart[0] = pl.s0; pl.npart[1] = n - pl.p1;
+  for (int p = 0; p < 2; ++p) {
+    pl.q[p] = (pl.npart[p] - mid_rows_min(kd)) / (2 * NB);
+    if (pl.npart[p] < mid_rows_min(kd) || pl.q[p] < bt + 2 || (mode < 2 && pl.q[p] < 2 * bt + 8)) return pl;
+    pl.r0[p] = pl.q[p] * NB; pl.nm[p] = pl.npart[p] - 2 * pl.r0[p]; pl.nph[p] = pl.npart[p] - pl.r0[p];
+    pl.ntm[p] = (pl.nm[p] + NB - 1) / NB; pl.npE[p] = pl.q[p] + pl.ntm[p]; pl.ldE[p] = pl.npE[p] * NB;
+  }
+  if (bt > SPK_MAX_BT || (w - 1 + NB - 1) / NB > CL_MAX_BT) return pl;
+  pl.ok = 1;
+  return pl;
 }
 
 }  // namespace ba

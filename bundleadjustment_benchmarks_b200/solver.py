@@ -53,6 +53,25 @@ class Trial:
     dx_norm: float
 
 
+_PLAN_LIB = None
+
+
+def split_plan(n: int, kd: int, mode: int = 1, segments: int = 3) -> dict:
+    """Host-side plan of the separator split of the band LDL^T for a reduced system of n rows and half-bandwidth kd
+    (ba_split_plan; pure arithmetic, runs without a GPU)."""
+    global _PLAN_LIB
+    if _PLAN_LIB is None:
+        _PLAN_LIB = _lib.lib()
+    out = np.zeros(24, dtype=np.int32)
+    rc = _PLAN_LIB.ba_split_plan(int(n), int(kd), int(mode), int(segments), out.ctypes.data_as(C.POINTER(C.c_int)), 24)
+    if rc != 0:
+        raise BAError(f"ba_split_plan failed ({rc})")
+    keys = ("ok", "w", "s0", "p1", "n0", "n1", "q0", "q1", "nm0", "nm1", "ntm0", "ntm1", "npE0", "npE1", "segments")
+    d = {k: int(v) for k, v in zip(keys, out[:15])}
+    d["bounds"] = [int(v) for v in out[15:15 + d["segments"] + 1]]
+    return d
+
+
 class GpuSolver:
     def __init__(self, prob, variant="QRCHOL", precision="f64", tau: float = 0.5, device: int = 0):
         self._L = _lib.lib()

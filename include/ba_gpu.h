@@ -112,6 +112,14 @@ int ba_step_streamed(ba_handle* h, const double* R, const double* T, const doubl
 int ba_accept(ba_handle* h);
 int ba_reject(ba_handle* h);
 
+/* Host-side plan of the separator split of the band LDL^T (no reference counterpart: the elimination order is the solver's own
+ * business, QRChol.h:197-206 only asks for the solution). Pure arithmetic, needs no GPU and no handle: for a reduced system of n
+ * rows and half-bandwidth kd, mode 0 / 1 / 2 (off / only when the chains are long enough / whenever possible) and 1..4 chain
+ * segments, out[0..23] = { split used, separator rows w, first separator row s0, first row of part 1, rows of part 0, rows of part 1,
+ * panels per chain of part 0 / part 1, middle-block rows of part 0 / 1, middle-block panels of part 0 / 1, spike panels of part 0 / 1,
+ * segments, first panel of every segment of part 0's chains (segments + 1 values), 0... }. */
+int ba_split_plan(int n, int kd, int mode, int segments, int* out, int out_len);
+
 /* ≙ Utils::showErrorStatistics + Utils::showObjective (src/Utils.h:15-68; bundle_adjustment_large.cpp:130-131,170-171) as one GPU
  * reduction at the device-resident state: sums[0] = sum_k avg_f |p_k - m_k|, sums[1] = the same over the inliers
  * (error <= inlier_threshold), sums[2] = number of inliers, sums[3] = "True objective" = sum_k psi(thr^2, avg_f^2 |p_k - m_k|)
